@@ -1,0 +1,467 @@
+// alpaka_b200/csrc/b200_heat2d.cu -- fused FTCS step of heatEquation2D for sm_100a.
+//
+// Replaces the two launches per step of the reference (example/heatEquation2D/src/heatEquation2D.cpp:141-168):
+//   StencilKernel<(16+2)*(16+2)> (StencilKernel.hpp:31-89): 16x16 tile + halo staged into shared memory by a
+//     per-thread linear-index loop with a div/mod per element (mapIdx, :59-65), one output cell per thread;
+//   BoundaryKernel (BoundaryKernel.hpp:24-86): a full-grid launch in which only edge blocks work, calling
+//     exp/sin per ring cell.
+// Here ONE persistent kernel per step:
+//   * the (TY+2) x (TX+4) input box of each 32 x 128 output tile is fetched by TMA (cp.async.bulk.tensor.2d,
+//     SASS UTMALDG) into a ring of shared-memory stages; one elected thread issues the copies and an mbarrier
+//     per stage carries the transaction count, so STAGES-1 tiles (~36 KB each) are always in flight per CTA
+//     while the 256 threads compute the current one. Out-of-range box parts are zero-filled by the TMA unit,
+//     so edge tiles need no address arithmetic.
+//   * each thread owns a column PAIR and walks 8 rows, keeping the 3x3 neighbourhood in registers: three
+//     16-byte LDS per row (conflict-free: a warp reads 512 contiguous bytes), one 16-byte coalesced global
+//     store per row. Tiles start on even columns so every store is 16-byte aligned although core cells start at
+//     column 1.
+//   * the boundary ring is written by the same kernel from separable host tables:
+//     exactSolution(x,y,t) = exp(-pi^2 t) * (sin(pi x) + sin(pi y)) == tf * (sx[i] + sy[j]) with sx, sy, tf computed
+//     on the host by glibc, which makes the ring (and therefore the whole field) bit-identical to the reference
+//     CPU back-end. Corners are never written, as in the reference.
+//   * arithmetic order is the reference's, ((((c*k + l*rX) + r*rX) + u*rY) + d*rY), with explicit
+//     __dmul_rn/__dadd_rn (no FMA contraction).
+// Roofline: HBM, 16 B per core cell per step (one read + one write); halo columns/rows re-read by neighbouring
+// tiles (1.096x at 32x128+halo) are served by the 126 MB L2 because neighbouring tiles are processed within the
+// same wave / the next tile-row (4 MB apart).
+#include "b200_common.cuh"
+
+#include <cuda.h> // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+
+#include <mutex>
+
+namespace
+{
+    constexpr int TX = 128; // output tile width  (cells)
+    constexpr int TY = 32; // output tile height (cells)
+    constexpr int BOX_X = TX + 4; // input box: 2 halo columns on each side (keeps 16-byte alignment of pairs)
+    constexpr int BOX_Y = TY + 2;
+    constexpr int BOX_BYTES = BOX_X * BOX_Y * 8; // 35904
+    constexpr int STAGE_BYTES = (BOX_BYTES + 127) / 128 * 128; // TMA destination must be 128-byte aligned
+    constexpr int kThreads = 256;
+    constexpr int kRowGroups = kThreads / (TX / 2); // 4
+    constexpr int kRowsPerThread = TY / kRowGroups; // 8
+    constexpr int kMaxStages = 6;
+
+    struct HeatArgs
+    {
+        double* dst;
+        size_t pitchElems;
+        uint32_t ny, nx;
+        uint32_t j0, j1, i0, i1; // output window, padded coordinates
+        uint32_t iw0; // i0 rounded down to even: tile grid origin
+        uint32_t tilesX, tilesY;
+        double k, rX, rY, tf;
+        double const* sx;
+        double const* sy;
+        int edges;
+        int stages;
+    };
+
+    __device__ __forceinline__ uint32_t smemAddr(void const* p)
+    {
+        return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+    }
+
+    __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+    }
+
+    __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes)
+                     : "memory");
+    }
+
+    __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra DONE_%=;\n"
+            "bra WAIT_%=;\n"
+            "DONE_%=:\n"
+            "}\n" ::"r"(smemAddr(bar)),
+            "r"(parity)
+            : "memory");
+    }
+
+    __device__ __forceinline__ void tmaLoad2d(void* smemDst, CUtensorMap const* map, int32_t cx, int32_t cy, uint64_t* bar)
+    {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+                "r"(smemAddr(smemDst)),
+            "l"(reinterpret_cast<uint64_t>(map)),
+            "r"(cx),
+            "r"(cy),
+            "r"(smemAddr(bar))
+            : "memory");
+    }
+
+    __device__ __forceinline__ double2 lds128(double const* p)
+    {
+        double2 v;
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(smemAddr(p)));
+        return v;
+    }
+
+    template<int HINT>
+    __device__ __forceinline__ void stg2(double* p, double a, double b)
+    {
+        if constexpr(HINT)
+            asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+        else
+            asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+    }
+
+    // StencilKernel.hpp:84-86, left to right, no contraction
+    __device__ __forceinline__ double ftcs(double c, double l, double r, double u, double d, double k, double rX, double rY)
+    {
+        double t = __dmul_rn(c, k);
+        t = __dadd_rn(t, __dmul_rn(l, rX));
+        t = __dadd_rn(t, __dmul_rn(r, rX));
+        t = __dadd_rn(t, __dmul_rn(u, rY));
+        t = __dadd_rn(t, __dmul_rn(d, rY));
+        return t;
+    }
+
+    // Value of a non-core cell, or "no write". BoundaryKernel.hpp:63-84: top/bottom rows for i in 1..nx, left/right
+    // columns for j in 1..ny; corners untouched. Sides not flagged in `edges` are ghost cells of a sub-domain.
+    __device__ __forceinline__ bool ringValue(HeatArgs const& A, uint32_t j, uint32_t i, double& v)
+    {
+        bool const rowRing = (j == 0 && (A.edges & B200_EDGE_TOP)) || (j == A.ny + 1 && (A.edges & B200_EDGE_BOTTOM));
+        bool const colRing = (i == 0 && (A.edges & B200_EDGE_LEFT)) || (i == A.nx + 1 && (A.edges & B200_EDGE_RIGHT));
+        bool const iCore = i >= 1 && i <= A.nx;
+        bool const jCore = j >= 1 && j <= A.ny;
+        if((rowRing && iCore) || (colRing && jCore))
+        {
+            v = __dmul_rn(A.tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
+            return true;
+        }
+        return false;
+    }
+
+    template<int HINT>
+    __global__ void __launch_bounds__(kThreads) heatStepKernel(const __grid_constant__ CUtensorMap mapSrc, HeatArgs const A)
+    {
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t full[kMaxStages];
+
+        uint32_t const totalTiles = A.tilesX * A.tilesY;
+        int const tid = threadIdx.x;
+        int const stages = A.stages;
+
+        auto tileOrigin = [&](uint32_t t, uint32_t& y0, uint32_t& x0)
+        {
+            uint32_t const ty = t / A.tilesX;
+            uint32_t const tx = t - ty * A.tilesX;
+            y0 = A.j0 + ty * TY;
+            x0 = A.iw0 + tx * TX;
+        };
+        auto issue = [&](uint32_t t, int s)
+        {
+            uint32_t y0, x0;
+            tileOrigin(t, y0, x0);
+            mbarExpectTx(&full[s], BOX_BYTES);
+            tmaLoad2d(smem + size_t(s) * STAGE_BYTES, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 1, &full[s]);
+        };
+
+        if(tid == 0)
+        {
+            for(int s = 0; s < stages; ++s)
+                mbarInit(&full[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if(tid == 0)
+        {
+            for(int s = 0; s < stages; ++s)
+            {
+                uint32_t const t = blockIdx.x + uint32_t(s) * gridDim.x;
+                if(t < totalTiles)
+                    issue(t, s);
+            }
+        }
+
+        int const cp = tid % (TX / 2); // column pair within the tile
+        int const rg = tid / (TX / 2); // row group
+        int s = 0;
+        uint32_t parity = 0;
+        for(uint32_t t = blockIdx.x; t < totalTiles; t += gridDim.x)
+        {
+            uint32_t y0, x0;
+            tileOrigin(t, y0, x0);
+            mbarWait(&full[s], parity);
+
+            double const* box = reinterpret_cast<double const*>(smem + size_t(s) * STAGE_BYTES);
+            // box(r, c): r = output row offset + 1, c = output col offset + 2
+            int const r0 = rg * kRowsPerThread;
+            double const* p = box + size_t(r0) * BOX_X + 2 * cp; // row above the first output row, left pair
+            double2 up = lds128(p + 2);
+            double2 cl = lds128(p + BOX_X), cc = lds128(p + BOX_X + 2), cr = lds128(p + BOX_X + 4);
+
+            uint32_t const gi = x0 + 2 * cp; // global (padded) column of the pair's first cell
+            bool const fast = y0 >= 1 && y0 + TY <= A.ny + 1 && y0 >= A.j0 && y0 + TY <= A.j1 && x0 >= 1
+                              && x0 + TX <= A.nx + 1 && x0 >= A.i0 && x0 + TX <= A.i1;
+            double* out = A.dst + size_t(y0 + r0) * A.pitchElems + gi;
+#pragma unroll
+            for(int r = 0; r < kRowsPerThread; ++r)
+            {
+                double const* q = p + size_t(r + 2) * BOX_X;
+                double2 const nl = lds128(q), nc = lds128(q + 2), nr = lds128(q + 4);
+                double const v0 = ftcs(cc.x, cl.y, cc.y, up.x, nc.x, A.k, A.rX, A.rY);
+                double const v1 = ftcs(cc.y, cc.x, cr.x, up.y, nc.y, A.k, A.rX, A.rY);
+                if(fast)
+                {
+                    stg2<HINT>(out, v0, v1);
+                }
+                else
+                {
+                    uint32_t const gj = y0 + r0 + r;
+                    bool w0 = false, w1 = false;
+                    double o0 = v0, o1 = v1;
+                    if(gj >= A.j0 && gj < A.j1 && gj <= A.ny + 1)
+                    {
+                        bool const jCore = gj >= 1 && gj <= A.ny;
+                        if(gi >= A.i0 && gi < A.i1 && gi <= A.nx + 1)
+                            w0 = (jCore && gi >= 1 && gi <= A.nx) ? true : ringValue(A, gj, gi, o0);
+                        if(gi + 1 >= A.i0 && gi + 1 < A.i1 && gi + 1 <= A.nx + 1)
+                            w1 = (jCore && gi + 1 >= 1 && gi + 1 <= A.nx) ? true : ringValue(A, gj, gi + 1, o1);
+                    }
+                    if(w0 && w1)
+                        stg2<HINT>(out, o0, o1);
+                    else if(w0)
+                        out[0] = o0;
+                    else if(w1)
+                        out[1] = o1;
+                }
+                up = cc;
+                cl = nl;
+                cc = nc;
+                cr = nr;
+                out += A.pitchElems;
+            }
+
+            __syncthreads(); // every thread is done reading stage s
+            if(tid == 0)
+            {
+                uint32_t const tn = t + uint32_t(stages) * gridDim.x;
+                if(tn < totalTiles)
+                    issue(tn, s);
+            }
+            if(++s == stages)
+            {
+                s = 0;
+                parity ^= 1u;
+            }
+        }
+    }
+
+    // ---- host side
+    using EncodeTiledFn = CUresult (*)(
+        CUtensorMap*,
+        CUtensorMapDataType,
+        cuuint32_t,
+        void*,
+        cuuint64_t const*,
+        cuuint64_t const*,
+        cuuint32_t const*,
+        cuuint32_t const*,
+        CUtensorMapInterleave,
+        CUtensorMapSwizzle,
+        CUtensorMapL2promotion,
+        CUtensorMapFloatOOBfill);
+
+    EncodeTiledFn encoder()
+    {
+        static EncodeTiledFn fn = nullptr;
+        static std::once_flag once;
+        std::call_once(
+            once,
+            []
+            {
+                void* p = nullptr;
+                cudaDriverEntryPointQueryResult q;
+                if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess
+                   && q == cudaDriverEntryPointSuccess)
+                    fn = reinterpret_cast<EncodeTiledFn>(p);
+                else
+                    (void) cudaGetLastError();
+            });
+        return fn;
+    }
+} // namespace
+
+struct b200_heat2d_plan_st
+{
+    int dev;
+    double* u[2];
+    size_t pitchBytes;
+    uint32_t ny, nx;
+    int edges;
+    double* sx;
+    double* sy;
+    CUtensorMap map[2];
+};
+
+extern "C"
+{
+    int b200_heat2d_plan_create(
+        int dev,
+        double* u0,
+        double* u1,
+        size_t pitch_bytes,
+        uint32_t ny,
+        uint32_t nx,
+        double const* sx_host,
+        double const* sy_host,
+        int edges,
+        b200_heat2d_plan_t* out)
+    {
+        B200_REQUIRE(out && u0 && u1 && sx_host && sy_host, B200_EINVAL);
+        B200_REQUIRE(ny >= 1 && nx >= 1 && (edges & ~B200_EDGE_ALL) == 0, B200_EINVAL);
+        B200_REQUIRE(pitch_bytes >= (size_t(nx) + 2) * 8, B200_EINVAL);
+        B200_REQUIRE(pitch_bytes % 16 == 0, B200_EALIGN);
+        B200_REQUIRE(reinterpret_cast<uintptr_t>(u0) % 16 == 0 && reinterpret_cast<uintptr_t>(u1) % 16 == 0, B200_EALIGN);
+        B200_REQUIRE(uint64_t(ny) + 2 + TY < 0x7fffffffull && uint64_t(nx) + 2 + TX < 0x7fffffffull, B200_ERANGE);
+        B200_CUDA(cudaSetDevice(dev));
+        EncodeTiledFn const enc = encoder();
+        if(!enc)
+            return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+
+        auto* plan = new b200_heat2d_plan_st{};
+        plan->dev = dev;
+        plan->u[0] = u0;
+        plan->u[1] = u1;
+        plan->pitchBytes = pitch_bytes;
+        plan->ny = ny;
+        plan->nx = nx;
+        plan->edges = edges;
+        for(int b = 0; b < 2; ++b)
+        {
+            cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(ny) + 2};
+            cuuint64_t const strides[1] = {cuuint64_t(pitch_bytes)};
+            cuuint32_t const box[2] = {BOX_X, BOX_Y};
+            cuuint32_t const estr[2] = {1, 1};
+            CUresult const r = enc(
+                &plan->map[b],
+                CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                2,
+                plan->u[b],
+                dims,
+                strides,
+                box,
+                estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if(r != CUDA_SUCCESS)
+            {
+                delete plan;
+                return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
+            }
+        }
+        size_t const bx = (size_t(nx) + 2) * 8, by = (size_t(ny) + 2) * 8;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&plan->sx), bx);
+        if(e == cudaSuccess)
+            e = cudaMalloc(reinterpret_cast<void**>(&plan->sy), by);
+        if(e == cudaSuccess)
+            e = cudaMemcpy(plan->sx, sx_host, bx, cudaMemcpyHostToDevice);
+        if(e == cudaSuccess)
+            e = cudaMemcpy(plan->sy, sy_host, by, cudaMemcpyHostToDevice);
+        if(e == cudaSuccess)
+            e = cudaFuncSetAttribute(heatStepKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
+        if(e == cudaSuccess)
+            e = cudaFuncSetAttribute(heatStepKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
+        if(e != cudaSuccess)
+        {
+            cudaFree(plan->sx);
+            cudaFree(plan->sy);
+            delete plan;
+            return b200::cudaFail(e, "heat2d plan setup", __FILE__, __LINE__);
+        }
+        *out = plan;
+        return 0;
+    }
+
+    int b200_heat2d_plan_destroy(b200_heat2d_plan_t plan)
+    {
+        if(!plan)
+            return 0;
+        B200_CUDA(cudaSetDevice(plan->dev));
+        B200_CUDA(cudaFree(plan->sx));
+        B200_CUDA(cudaFree(plan->sy));
+        delete plan;
+        return 0;
+    }
+
+    int b200_heat2d_step_window_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        double time_factor,
+        uint32_t j0,
+        uint32_t j1,
+        uint32_t i0,
+        uint32_t i1)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1), B200_EINVAL);
+        B200_REQUIRE(j1 <= plan->ny + 2 && i1 <= plan->nx + 2, B200_EINVAL);
+        if(j0 >= j1 || i0 >= i1)
+            return 0;
+        HeatArgs A{};
+        A.dst = plan->u[1 - src_index];
+        A.pitchElems = plan->pitchBytes / 8;
+        A.ny = plan->ny;
+        A.nx = plan->nx;
+        A.j0 = j0;
+        A.j1 = j1;
+        A.i0 = i0;
+        A.i1 = i1;
+        A.iw0 = i0 & ~1u;
+        A.tilesX = (i1 - A.iw0 + TX - 1) / TX;
+        A.tilesY = (j1 - j0 + TY - 1) / TY;
+        // StencilKernel.hpp:84: (1.0 - 2.0 * rX - 2.0 * rY), evaluated left to right in IEEE double on the host
+        // (this TU is built with -ffp-contract=off for host code)
+        A.rX = rx;
+        A.rY = ry;
+        A.k = 1.0 - 2.0 * rx - 2.0 * ry;
+        A.tf = time_factor;
+        A.sx = plan->sx;
+        A.sy = plan->sy;
+        A.edges = plan->edges;
+        int stages = int(b200::tune("heat.stages", 3));
+        if(stages < 1)
+            stages = 1;
+        if(stages > kMaxStages)
+            stages = kMaxStages;
+        A.stages = stages;
+        int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 2));
+        int const hint = int(b200::tune("heat.hint", 1));
+        uint64_t const total = uint64_t(A.tilesX) * A.tilesY;
+        B200_REQUIRE(total < 0xffffffffull, B200_ERANGE);
+        uint64_t grid = uint64_t(b200::smCount(plan->dev)) * (ctasPerSm > 0 ? ctasPerSm : 1);
+        if(grid > total)
+            grid = total;
+        auto const s = reinterpret_cast<cudaStream_t>(stream);
+        size_t const smemBytes = size_t(stages) * STAGE_BYTES;
+        if(hint)
+            heatStepKernel<1><<<unsigned(grid), kThreads, smemBytes, s>>>(plan->map[src_index], A);
+        else
+            heatStepKernel<0><<<unsigned(grid), kThreads, smemBytes, s>>>(plan->map[src_index], A);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int b200_heat2d_step_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor)
+    {
+        B200_REQUIRE(plan, B200_EINVAL);
+        return b200_heat2d_step_window_f64(plan, s, src_index, rx, ry, time_factor, 0, plan->ny + 2, 0, plan->nx + 2);
+    }
+}

@@ -1,0 +1,444 @@
+// alpaka_b200/csrc/b200_stream.cu -- BabelStream Init/Copy/Mul/Add/Triad/Nstream for sm_100a.
+//
+// Replaces the user functors of the reference driver (benchmarks/babelstream/src/babelStreamMainTest.cpp:
+// InitKernel :53-69, CopyKernel :72-86, MultKernel :89-104, AddKernel :107-122, TriadKernel :125-141) which the
+// reference runs one element per thread through its generic trampoline (scalar LDG.E.64 / STG.E.64).
+// Here: HBM-bound streams, so the design is about bytes in flight and full-width transactions:
+//   * each thread moves UNROLL vectors of VB = 32 bytes (ld/st.global.v4.b64, new with sm_100) or 16 bytes,
+//     all loads of an iteration issued before the first store;
+//   * a block owns a contiguous chunk of blockDim*UNROLL vectors per iteration, a warp access is one
+//     contiguous 512 B / 1 KiB span (fully coalesced, 4 or 8 sectors per request per thread);
+//   * grid = SMs x ctas_per_sm persistent blocks striding over chunks (or one block per chunk);
+//   * streaming cache policy (ld.global.nc.L1::no_allocate, st.global.cs) because nothing is re-used;
+//   * arithmetic is __dmul_rn/__dadd_rn (__fmul_rn/__fadd_rn): FMA contraction pinned OFF so the bits equal the
+//     reference CPU back-end compiled with -ffp-contract=off.
+// Algorithmic bytes per element: Init 24 (f64) / 12 (f32), Copy/Mul 16/8, Add/Triad 24/12,
+// Nstream 32/16.
+#include "b200_common.cuh"
+
+namespace
+{
+    using b200::ldg128;
+    using b200::ldg256;
+    using b200::stg128;
+    using b200::stg256;
+
+    // ---- a VB-byte pack of T held in registers
+    template<typename T, int VB>
+    struct Pack
+    {
+        static constexpr int N = VB / int(sizeof(T));
+        T v[N];
+    };
+
+    template<int HINT, typename T, int VB>
+    __device__ __forceinline__ Pack<T, VB> loadPack(T const* base, uint64_t vecIdx)
+    {
+        Pack<T, VB> p;
+        T const* ptr = base + vecIdx * uint64_t(Pack<T, VB>::N);
+        if constexpr(VB == 32)
+        {
+            uint64_t r[4];
+            ldg256<HINT>(ptr, r);
+            memcpy(p.v, r, 32);
+        }
+        else if constexpr(VB == 16)
+        {
+            uint32_t r[4];
+            ldg128<HINT>(ptr, r);
+            memcpy(p.v, r, 16);
+        }
+        else
+        {
+            static_assert(VB == int(sizeof(T)));
+            p.v[0] = *ptr;
+        }
+        return p;
+    }
+
+    template<int HINT, typename T, int VB>
+    __device__ __forceinline__ void storePack(T* base, uint64_t vecIdx, Pack<T, VB> const& p)
+    {
+        T* ptr = base + vecIdx * uint64_t(Pack<T, VB>::N);
+        if constexpr(VB == 32)
+        {
+            uint64_t r[4];
+            memcpy(r, p.v, 32);
+            stg256<HINT>(ptr, r);
+        }
+        else if constexpr(VB == 16)
+        {
+            uint32_t r[4];
+            memcpy(r, p.v, 16);
+            stg128<HINT>(ptr, r);
+        }
+        else
+        {
+            *ptr = p.v[0];
+        }
+    }
+
+    __device__ __forceinline__ double mulRn(double a, double b)
+    {
+        return __dmul_rn(a, b);
+    }
+
+    __device__ __forceinline__ float mulRn(float a, float b)
+    {
+        return __fmul_rn(a, b);
+    }
+
+    __device__ __forceinline__ double addRn(double a, double b)
+    {
+        return __dadd_rn(a, b);
+    }
+
+    __device__ __forceinline__ float addRn(float a, float b)
+    {
+        return __fadd_rn(a, b);
+    }
+
+    // ---- the six operations. In<VB> = what one vector step loads; apply() stores.
+    template<typename T>
+    struct InitOp
+    {
+        T* a;
+        T* b;
+        T* c;
+        T initA;
+
+        template<int VB>
+        struct In
+        {
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t) const
+        {
+            return {};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const&) const
+        {
+            Pack<T, VB> pa, pz;
+#pragma unroll
+            for(int k = 0; k < Pack<T, VB>::N; ++k)
+            {
+                pa.v[k] = initA;
+                pz.v[k] = T(0.0);
+            }
+            storePack<HINT>(a, i, pa);
+            storePack<HINT>(b, i, pz);
+            storePack<HINT>(c, i, pz);
+        }
+    };
+
+    template<typename T>
+    struct CopyOp
+    {
+        T const* a;
+        T* b;
+
+        template<int VB>
+        struct In
+        {
+            Pack<T, VB> a;
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t i) const
+        {
+            return {loadPack<HINT, T, VB>(a, i)};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const& in) const
+        {
+            storePack<HINT>(b, i, in.a);
+        }
+    };
+
+    template<typename T>
+    struct MulOp
+    {
+        T const* a;
+        T* b;
+        T scalar;
+
+        template<int VB>
+        struct In
+        {
+            Pack<T, VB> a;
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t i) const
+        {
+            return {loadPack<HINT, T, VB>(a, i)};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const& in) const
+        {
+            Pack<T, VB> o;
+#pragma unroll
+            for(int k = 0; k < Pack<T, VB>::N; ++k)
+                o.v[k] = mulRn(scalar, in.a.v[k]);
+            storePack<HINT>(b, i, o);
+        }
+    };
+
+    template<typename T>
+    struct AddOp
+    {
+        T const* a;
+        T const* b;
+        T* c;
+
+        template<int VB>
+        struct In
+        {
+            Pack<T, VB> a, b;
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t i) const
+        {
+            return {loadPack<HINT, T, VB>(a, i), loadPack<HINT, T, VB>(b, i)};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const& in) const
+        {
+            Pack<T, VB> o;
+#pragma unroll
+            for(int k = 0; k < Pack<T, VB>::N; ++k)
+                o.v[k] = addRn(in.a.v[k], in.b.v[k]);
+            storePack<HINT>(c, i, o);
+        }
+    };
+
+    template<typename T>
+    struct TriadOp
+    {
+        T const* a;
+        T const* b;
+        T* c;
+        T scalar;
+
+        template<int VB>
+        struct In
+        {
+            Pack<T, VB> a, b;
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t i) const
+        {
+            return {loadPack<HINT, T, VB>(a, i), loadPack<HINT, T, VB>(b, i)};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const& in) const
+        {
+            Pack<T, VB> o;
+#pragma unroll
+            for(int k = 0; k < Pack<T, VB>::N; ++k)
+                o.v[k] = addRn(in.a.v[k], mulRn(scalar, in.b.v[k]));
+            storePack<HINT>(c, i, o);
+        }
+    };
+
+    template<typename T>
+    struct NstreamOp
+    {
+        T* a;
+        T const* b;
+        T const* c;
+        T scalar;
+
+        template<int VB>
+        struct In
+        {
+            Pack<T, VB> a, b, c;
+        };
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ In<VB> load(uint64_t i) const
+        {
+            // `a` is read-modify-write: it must not go through the non-coherent path
+            return {loadPack<0, T, VB>(a, i), loadPack<HINT, T, VB>(b, i), loadPack<HINT, T, VB>(c, i)};
+        }
+
+        template<int HINT, int VB>
+        __device__ __forceinline__ void apply(uint64_t i, In<VB> const& in) const
+        {
+            Pack<T, VB> o;
+#pragma unroll
+            for(int k = 0; k < Pack<T, VB>::N; ++k)
+                o.v[k] = addRn(in.a.v[k], addRn(in.b.v[k], mulRn(scalar, in.c.v[k])));
+            storePack<HINT>(a, i, o);
+        }
+    };
+
+    // ---- the kernel: persistent (or one-chunk-per-block) grid-stride over chunks of blockDim*UNROLL vectors
+    template<typename Op, typename T, int VB, int UNROLL, int HINT>
+    __global__ void __launch_bounds__(512) streamKernel(Op const op, uint64_t const nVec, uint64_t const n)
+    {
+        using In = typename Op::template In<VB>;
+        uint64_t const chunk = uint64_t(blockDim.x) * UNROLL;
+        uint64_t const nFull = nVec / chunk;
+
+        for(uint64_t c = blockIdx.x; c < nFull; c += gridDim.x)
+        {
+            uint64_t const base = c * chunk + threadIdx.x;
+            In in[UNROLL];
+#pragma unroll
+            for(int u = 0; u < UNROLL; ++u)
+                in[u] = op.template load<HINT, VB>(base + uint64_t(u) * blockDim.x);
+#pragma unroll
+            for(int u = 0; u < UNROLL; ++u)
+                op.template apply<HINT, VB>(base + uint64_t(u) * blockDim.x, in[u]);
+        }
+
+        // partial last chunk: the block whose turn it would be
+        if(blockIdx.x == nFull % gridDim.x)
+        {
+            for(uint64_t i = nFull * chunk + threadIdx.x; i < nVec; i += blockDim.x)
+            {
+                In const in = op.template load<HINT, VB>(i);
+                op.template apply<HINT, VB>(i, in);
+            }
+            // scalar tail: fewer than one vector of elements
+            constexpr int N = Pack<T, VB>::N;
+            uint64_t const tailStart = nVec * N;
+            if constexpr(N > 1)
+            {
+                if(tailStart + threadIdx.x < n)
+                {
+                    using In1 = typename Op::template In<int(sizeof(T))>;
+                    In1 const in = op.template load<0, int(sizeof(T))>(tailStart + threadIdx.x);
+                    op.template apply<0, int(sizeof(T))>(tailStart + threadIdx.x, in);
+                }
+            }
+        }
+    }
+
+    struct StreamCfg
+    {
+        int vb, unroll, hint, block, ctasPerSm;
+    };
+
+    StreamCfg streamCfg(char const* opName, int elemBytes)
+    {
+        (void) elemBytes;
+        StreamCfg c;
+        std::string const p = std::string("stream.") + opName + ".";
+        c.vb = int(b200::tune((p + "vb").c_str(), b200::tune("stream.vb", 32)));
+        c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", 2)));
+        c.hint = int(b200::tune((p + "hint").c_str(), b200::tune("stream.hint", 1)));
+        c.block = int(b200::tune((p + "block").c_str(), b200::tune("stream.block", 512)));
+        c.ctasPerSm = int(b200::tune((p + "ctas_per_sm").c_str(), b200::tune("stream.ctas_per_sm", 4)));
+        return c;
+    }
+
+    template<typename Op, typename T, int VB, int UNROLL, int HINT>
+    int launchOne(cudaStream_t s, Op const& op, uint64_t n, StreamCfg const& cfg)
+    {
+        constexpr int N = Pack<T, VB>::N;
+        uint64_t const nVec = n / N;
+        uint64_t const chunk = uint64_t(cfg.block) * UNROLL;
+        uint64_t const nChunks = (nVec + chunk - 1) / chunk;
+        uint64_t grid = nChunks ? nChunks : 1;
+        if(cfg.ctasPerSm > 0)
+        {
+            uint64_t const persistent = uint64_t(b200::smCount(b200::currentDevice())) * cfg.ctasPerSm;
+            grid = grid < persistent ? grid : persistent;
+        }
+        if(grid > 0x7fffffffull)
+            grid = 0x7fffffffull;
+        streamKernel<Op, T, VB, UNROLL, HINT><<<unsigned(grid), cfg.block, 0, s>>>(op, nVec, n);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
+
+    template<typename Op, typename T, int VB, int HINT>
+    int launchUnroll(cudaStream_t s, Op const& op, uint64_t n, StreamCfg const& cfg)
+    {
+        switch(cfg.unroll)
+        {
+        case 1:
+            return launchOne<Op, T, VB, 1, HINT>(s, op, n, cfg);
+        case 2:
+            return launchOne<Op, T, VB, 2, HINT>(s, op, n, cfg);
+        case 4:
+            return launchOne<Op, T, VB, 4, HINT>(s, op, n, cfg);
+        default:
+            return b200::fail(B200_EINVAL, "stream.unroll must be 1, 2 or 4", __FILE__, __LINE__);
+        }
+    }
+
+    template<typename Op, typename T>
+    int launchStream(b200_stream_t stream, Op const& op, uint64_t n, bool aligned32, bool aligned16, char const* name)
+    {
+        if(n == 0)
+            return 0;
+        auto const s = reinterpret_cast<cudaStream_t>(stream);
+        StreamCfg cfg = streamCfg(name, int(sizeof(T)));
+        if(cfg.block < 32 || cfg.block > 512 || cfg.block % 32 != 0)
+            return b200::fail(B200_EINVAL, "stream.block must be a multiple of 32 in [32,512]", __FILE__, __LINE__);
+        int vb = cfg.vb;
+        if(vb == 32 && !aligned32)
+            vb = 16;
+        if(vb == 16 && !aligned16)
+            vb = int(sizeof(T));
+        if(vb == 32)
+            return cfg.hint ? launchUnroll<Op, T, 32, 1>(s, op, n, cfg) : launchUnroll<Op, T, 32, 0>(s, op, n, cfg);
+        if(vb == 16)
+            return cfg.hint ? launchUnroll<Op, T, 16, 1>(s, op, n, cfg) : launchUnroll<Op, T, 16, 0>(s, op, n, cfg);
+        // element-aligned only: scalar path (still on the GPU; there is no CPU fallback)
+        return launchUnroll<Op, T, int(sizeof(T)), 0>(s, op, n, cfg);
+    }
+
+    template<typename... P>
+    bool alignedTo(size_t a, P... ptrs)
+    {
+        return (((reinterpret_cast<uintptr_t>(ptrs)) % a == 0) && ...);
+    }
+} // namespace
+
+#define B200_STREAM_ENTRIES(T, SFX)                                                                                   \
+    extern "C" int b200_stream_init_##SFX(b200_stream_t s, T* a, T* b, T* c, T init_a, uint64_t n)                    \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b && c), B200_EINVAL);                                                           \
+        return launchStream<InitOp<T>, T>(s, InitOp<T>{a, b, c, init_a}, n, alignedTo(32, a, b, c), alignedTo(16, a, b, c), "init"); \
+    }                                                                                                                 \
+    extern "C" int b200_stream_copy_##SFX(b200_stream_t s, T const* a, T* b, uint64_t n)                              \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b), B200_EINVAL);                                                                \
+        return launchStream<CopyOp<T>, T>(s, CopyOp<T>{a, b}, n, alignedTo(32, a, b), alignedTo(16, a, b), "copy");   \
+    }                                                                                                                 \
+    extern "C" int b200_stream_mul_##SFX(b200_stream_t s, T const* a, T* b, T scalar, uint64_t n)                     \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b), B200_EINVAL);                                                                \
+        return launchStream<MulOp<T>, T>(s, MulOp<T>{a, b, scalar}, n, alignedTo(32, a, b), alignedTo(16, a, b), "mul"); \
+    }                                                                                                                 \
+    extern "C" int b200_stream_add_##SFX(b200_stream_t s, T const* a, T const* b, T* c, uint64_t n)                   \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b && c), B200_EINVAL);                                                           \
+        return launchStream<AddOp<T>, T>(s, AddOp<T>{a, b, c}, n, alignedTo(32, a, b, c), alignedTo(16, a, b, c), "add"); \
+    }                                                                                                                 \
+    extern "C" int b200_stream_triad_##SFX(b200_stream_t s, T const* a, T const* b, T* c, T scalar, uint64_t n)       \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b && c), B200_EINVAL);                                                           \
+        return launchStream<TriadOp<T>, T>(s, TriadOp<T>{a, b, c, scalar}, n, alignedTo(32, a, b, c), alignedTo(16, a, b, c), "triad"); \
+    }                                                                                                                 \
+    extern "C" int b200_stream_nstream_##SFX(b200_stream_t s, T* a, T const* b, T const* c, T scalar, uint64_t n)     \
+    {                                                                                                                 \
+        B200_REQUIRE(n == 0 || (a && b && c), B200_EINVAL);                                                           \
+        return launchStream<NstreamOp<T>, T>(s, NstreamOp<T>{a, b, c, scalar}, n, alignedTo(32, a, b, c), alignedTo(16, a, b, c), "nstream"); \
+    }
+
+B200_STREAM_ENTRIES(double, f64)
+B200_STREAM_ENTRIES(float, f32)

@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- BabelStream Triad (headline) + the rest of the hot path on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's own CPU implementation (oracle/_ref) on the host cores
+
+Contract (see DESIGN.md "Measurement"):
+  * a STEP is one Triad pass c = a + 2*b over double arrays of 2^30 elements per GPU (BASELINE.json configs[1]); the
+    arrays (25.8 GB per GPU) are far larger than the 126 MB L2, so no flush is needed between iterations;
+  * `value` = whole-job Triad GB/s (24 B/element, all ranks) with inputs resident in HBM, timed with CUDA events on
+    the launching stream, barrier + synchronize on both sides, max over ranks;
+  * `roofline` = the Triad kernel's algorithmic bytes per launch / its average launch duration vs the measured HBM
+    copy bandwidth (MEASURED_PEAKS.json);
+  * `e2e` = the same Triad through the public host API with HOST buffers (pinned), H2D and D2H inside the timed
+    region, chunk-pipelined over 4 streams;
+  * `kernels` = every other kernel of the path (Init/Copy/Mul/Add/Nstream/Dot, reduce u32/f32, heatEquation2D) timed
+    the same way, as absolute GB/s and fraction of the HBM roofline;
+  * `cpu_baseline` = the reference's AccCpuOmp2Blocks Triad (oracle/_ref) on the host cores, bounded sample.
+Nothing here reads /root/reference at run time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import shutil
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "babelstream_triad_gbs"
+UNIT = "GB/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback"
+
+
+# ----------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        exe = shutil.which("nvidia-smi")
+        if not exe:
+            return
+        try:
+            self.proc = subprocess.Popen(
+                [exe, f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def host_mem_available_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for line in f:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) / 1e6
+    except Exception:
+        pass
+    return 0.0
+
+
+def time_reference_triad(n: int, runs: int):
+    """Reference TriadKernel on AccCpuOmp2Blocks (oracle/_ref), timed the reference's way (host clock around
+    exec + wait, babelStreamMainTest.cpp:279-291). Returns list of seconds per run, threads used."""
+    import oracle_lib as ol
+
+    L = ol.ref()
+    if L is None:
+        return None, 0, "oracle/_ref/libalpaka_ref.so missing"
+    secs = (C.c_double * runs)()
+    rc = L.ref_babelstream_time(4, 1, n, runs, secs, 0)
+    if rc != 0:
+        return None, 0, f"ref_babelstream_time rc={rc}"
+    return list(secs), L.ref_omp_max_threads(), None
+
+
+def time_port_triad(n: int, runs: int):
+    """Fallback CPU baseline: the plain-C oracle port (OpenMP) when oracle/_ref is unavailable."""
+    import numpy as np
+    import oracle_lib as ol
+
+    L = ol.oracle()
+    a, b, c = np.ones(n), np.full(n, 2.0), np.zeros(n)
+    out = []
+    for _ in range(runs):
+        t0 = time.perf_counter()
+        L.orc_triad_f64(ol.P(a), ol.P(b), ol.P(c), 2.0, n)
+        out.append(time.perf_counter() - t0)
+    return out, host_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n_full = 1 << 30
+    n = args.n or n_full
+    # 3 arrays of n doubles must fit the host comfortably
+    while 3 * 8 * n / 1e9 > 0.5 * host_mem_available_gb() and n > (1 << 22):
+        n //= 2
+    runs = args.warmup + args.steps
+    kind = "reference"
+    secs, threads, err = time_reference_triad(n, runs)
+    if secs is None:
+        kind = "port"
+        secs, threads = time_port_triad(n, runs)
+    timed = secs[args.warmup:]
+    mean_s = sum(timed) / len(timed)
+    value = 24.0 * n * 1e-9 / mean_s
+    sample = (f"reference TriadKernel (babelStreamMainTest.cpp:125-141) on AccCpuOmp2Blocks<1,uint32>, double, "
+              f"n=2^{n.bit_length() - 1} per step, {threads} OpenMP threads, host clock around exec+wait; "
+              f"best step {24.0 * n * 1e-9 / min(timed):.1f} GB/s")
+    if kind == "port":
+        sample = f"oracle C port (OpenMP) because: {err}; n={n}"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "BabelStream Triad double, 2^30 elements/array per GPU (BASELINE.json configs[1])",
+                   "elements_per_step": n, "bytes_per_element": 24},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+
+    import alpaka_b200 as ab
+    from alpaka_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    platform = ab.Platform()
+    if platform.get_dev_count() <= local_rank:
+        raise RuntimeError("bench.py needs one CUDA device per rank; alpaka_b200 has no CPU fallback")
+    dev = platform.get_dev_by_idx(local_rank)
+    q = ab.Queue(dev)
+    lib = _lib.load()
+    peak, peak_kind = measured_peak()
+
+    def barrier():
+        q.wait()
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e0, e1 = ab.Event(dev, timing=True), ab.Event(dev, timing=True)
+
+    def timed(fn, steps, warmup):
+        """W untimed + exactly K timed launches between barriers; CUDA events on the launching stream."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ab.enqueue(q, e0)
+        for _ in range(steps):
+            fn()
+        ab.enqueue(q, e1)
+        q.wait()
+        ms = e0.elapsed_ms(e1)
+        barrier()
+        return max_over_ranks(ms) / steps
+
+    n = args.n or (1 << 30)
+    K, W = args.steps, max(args.warmup, 3)
+    bs = ab.babelstream
+
+    a, b, c = (ab.alloc_buf(dev, np.float64, n, q) for _ in range(3))
+    # the driver's own data: a = 1, then b = 2 (Copy + Mult), c = 5 after Triad (babelStreamMainTest.cpp:305-339)
+    bs.init(q, a, b, c)
+    bs.copy(q, a, b)
+    bs.mul(q, a, b)
+    q.wait()
+
+    # ---- headline: Triad
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ab.runtime.launch_count()
+    ms_triad = timed(lambda: bs.triad(q, a, b, c), K, W)
+    launches = ab.runtime.launch_count() - launches0 - W
+    clocks = sampler.stop() if rank == 0 else None
+    triad_bytes = 24.0 * n
+    value = world * triad_bytes * 1e-9 / (ms_triad * 1e-3)
+
+    # spot-check the result the timed kernel produced (c must be 1 + 2*2 = 5 everywhere in a sampled window)
+    chk = np.empty(1 << 16)
+    ab.memcpy(q, chk, ab.create_view(dev, c.ptr + 8 * (n - (1 << 16)), np.float64, 1 << 16))
+    q.wait()
+    assert (chk == 5.0).all(), "Triad result check failed"
+
+    # ---- every other kernel of the path, same timing method (fewer steps for the long ones)
+    kernels = {}
+
+    def record(name, ms, nbytes):
+        gbs = world * nbytes * 1e-9 / (ms * 1e-3)
+        kernels[name] = {"gbs": round(gbs, 1), "ms": round(ms, 4), "frac_of_hbm_peak": round(gbs / world / peak, 4)}
+
+    record("triad_f64", ms_triad, triad_bytes)
+    if not args.quick:
+        Ks = max(5, K // 2)
+        record("init_f64", timed(lambda: bs.init(q, a, b, c), Ks, 3), 24.0 * n)
+        bs.copy(q, a, b)
+        bs.mul(q, a, b)
+        record("copy_f64", timed(lambda: bs.copy(q, a, c), Ks, 3), 16.0 * n)
+        record("mul_f64", timed(lambda: bs.mul(q, a, b), Ks, 3), 16.0 * n)
+        record("add_f64", timed(lambda: bs.add(q, a, b, c), Ks, 3), 24.0 * n)
+        record("nstream_f64", timed(lambda: bs.nstream(q, c, a, b, 0.0), Ks, 3), 32.0 * n)
+        out = ab.alloc_buf(dev, np.float64, 1, q)
+        record("dot_f64", timed(lambda: bs.dot_async(q, a, b, out), Ks, 3), 16.0 * n)
+        dot_local = np.empty(1)
+        ab.memcpy(q, dot_local, out)
+        q.wait()
+        dot_total = float(dot_local[0])
+        if dist is not None:
+            # Dot's exchange step: one scalar per GPU, combined in rank order for bit-stable results
+            import torch
+
+            mine = torch.tensor([dot_local[0]], dtype=torch.float64, device=f"cuda:{local_rank}")
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            dot_total = float(sum(float(p.item()) for p in parts))
+        assert dot_total == 2.0 * n * world, f"Dot check failed: {dot_total} != {2.0 * n * world}"
+        out.free()
+
+    for buf in (a, b, c):
+        buf.free()
+    q.wait()
+
+    if not args.quick:
+        # ---- example/reduce: 2^32 uint32 (17.2 GB) and 2^30 float (BASELINE.json configs[2])
+        nr = (1 << 32) if not args.n else 4 * n
+        src = ab.alloc_buf(dev, np.uint32, nr, q)
+        res = ab.alloc_buf(dev, np.uint32, 1, q)
+        # fill with ones via the f32 init kernel's bit pattern is not exact for u32; memset 0x01010101 instead
+        ab.memset(q, src, 1)
+        Ks = max(5, K // 2)
+        record("reduce_u32", timed(lambda: ab.reduce.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+        got = np.empty(1, dtype=np.uint32)
+        ab.memcpy(q, got, res)
+        q.wait()
+        assert int(got[0]) == (0x01010101 * nr) % 2**32, "reduce u32 check failed"
+        src.free()
+        res.free()
+        nf = (1 << 30) if not args.n else n
+        srcf = ab.alloc_buf(dev, np.float32, nf, q)
+        resf = ab.alloc_buf(dev, np.float32, 1, q)
+        ab.memset(q, srcf, 0)
+        record("reduce_f32", timed(lambda: ab.reduce.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+        for bf in (srcf, resf):
+            bf.free()
+
+        # ---- heatEquation2D 16384^2 double (BASELINE.json configs[3]); 16 B per core cell per step
+        ny = nx = args.heat or 16384
+        dx, dy = 1.0 / (nx + 1), 1.0 / (ny + 1)
+        dt = 0.2 * min(dx * dx, dy * dy)
+        h = ab.heat2d.Heat2D(q, ny, nx, dx, dy, dt)
+        lib.b200_memset2d_async(dev.idx, h.bufs[0].ptr, h.bufs[0].pitch_bytes, 0, (nx + 2) * 8, ny + 2, q.handle)
+        lib.b200_memset2d_async(dev.idx, h.bufs[1].ptr, h.bufs[1].pitch_bytes, 0, (nx + 2) * 8, ny + 2, q.handle)
+        record("heat2d_f64", timed(lambda: h.step(1), max(20, K), 5), 16.0 * ny * nx)
+        h.close()
+        q.wait()
+
+    # ---- e2e: Triad through the public host API, pinned HOST buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        ne = args.e2e_n or n
+        while 3 * 8 * ne / 1e9 > 0.4 * host_mem_available_gb() / max(world, 1) and ne > (1 << 24):
+            ne //= 2
+        ha, hb, hc = (ab.alloc_mapped_buf(np.float64, ne) for _ in range(3))
+        ha.array[:] = 1.0
+        hb.array[:] = 2.0
+        pipe = bs.TriadHostPipeline(dev, np.float64)
+        pipe.run(ha.array, hb.array, hc.array)  # warm-up
+        barrier()
+        steps_e = max(1, min(K, 3))
+        t0 = time.perf_counter()
+        for _ in range(steps_e):
+            h2d, d2h = pipe.run(ha.array, hb.array, hc.array)
+        t_e = (time.perf_counter() - t0) / steps_e
+        t_e = max_over_ranks(t_e)
+        assert float(hc.array[0]) == 5.0 and float(hc.array[-1]) == 5.0
+        e2e = {"value": world * 24.0 * ne * 1e-9 / t_e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "elements_per_step": ne, "steps": steps_e, "ms_per_step": t_e * 1e3,
+               "how": "pinned host arrays -> 4-stream chunk pipeline (H2D a,b; Triad; D2H c), wall clock incl. sync"}
+        pipe.close()
+        del ha, hb, hc
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): reference AccCpuOmp2Blocks Triad at C1's 2^25
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        n_cpu, runs = 1 << 25, 21
+        secs, threads, err = time_reference_triad(n_cpu, runs)
+        kind = "reference"
+        if secs is None:
+            kind = "port"
+            secs, threads = time_port_triad(n_cpu, runs)
+        best = min(secs[1:])
+        cpu = {"value": 24.0 * n_cpu * 1e-9 / best, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"Triad double n=2^25 (BASELINE.json configs[0]), {runs} runs, min excluding the first "
+                         f"(reference method), AccCpuOmp2Blocks" + ("" if kind == "reference" else f" [port: {err}]")}
+
+    if rank == 0:
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "triad_traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        achieved = triad_bytes * 1e-9 / (ms_triad * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_triad, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "BabelStream Triad double, 2^30 elements/array per GPU (BASELINE.json configs[1])",
+                       "elements_per_gpu": n, "bytes_per_element": 24,
+                       "l2": "inputs (25.8 GB per GPU) larger than L2, no flush needed",
+                       "parallelism": f"slab x{world}" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_kind": f"{peak_kind} (burst copy figure; kernel timed alone)",
+                         "kernel": "streamKernel<TriadOp<double>>"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=0, help="elements per array per GPU (default 2^30)")
+    ap.add_argument("--heat", type=int, default=0, help="heat2d grid edge (default 16384)")
+    ap.add_argument("--e2e-n", type=int, default=0)
+    ap.add_argument("--quick", action="store_true", help="Triad only")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

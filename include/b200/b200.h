@@ -1,0 +1,304 @@
+/* include/b200/b200.h -- C ABI of libalpaka_b200.so: the B200-native runtime + hand-written sm_100a kernels
+ * underneath alpaka's accelerator/trait API.
+ *
+ * This is the drop-in boundary. The reference (alpaka) reaches CUDA through a struct of static inline
+ * wrappers, `alpaka::ApiCudaRt` (include/alpaka/core/ApiCudaRt.hpp:107-396), called from its trait
+ * specialisations; its only device entry point is the generic trampoline
+ * `alpaka::detail::gpuKernel` (include/alpaka/kernel/TaskKernelGpuUniformCudaHipRt.hpp:61-76).
+ * Here the same trait specialisations (include/alpaka/, C++20) call the functions below instead: plain
+ * pointers, sizes and opaque handles, no C++ or torch types. Each entry cites the reference interface it
+ * replaces. Paths are relative to the reference root.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a positive cudaError_t value for CUDA failures, or a negative
+ *    B200_E* code; b200_last_error_string() describes the last failure on the calling thread (the
+ *    reference throws std::runtime_error with the same text from ALPAKA_UNIFORM_CUDA_HIP_RT_CHECK,
+ *    core/UniformCudaHip.hpp:23-112; the C++ layer above re-throws).
+ *  - like the reference, every call selects its device first (cudaSetDevice; e.g.
+ *    kernel/TaskKernelGpuUniformCudaHipRt.hpp:265); kernel entries take the stream and run on the device
+ *    the stream belongs to.
+ *  - kernel entries are asynchronous: they enqueue on `stream` and return.
+ *  - there is NO CPU fallback anywhere: without a CUDA device every entry that needs one fails.
+ */
+#ifndef B200_B200_H
+#define B200_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define B200_ABI_VERSION 1
+
+    /* negative (non-CUDA) error codes */
+#define B200_EINVAL (-1) /* bad argument (null pointer, zero size where not allowed, bad enum) */
+#define B200_EALIGN (-2) /* pointer / pitch alignment the kernel requires is not met */
+#define B200_ENODEV (-3) /* no CUDA device / driver entry point unavailable */
+#define B200_ERANGE (-4) /* extent does not fit the kernel's index range */
+
+    typedef struct b200_stream_st* b200_stream_t; /* == cudaStream_t */
+    typedef struct b200_event_st* b200_event_t; /* == cudaEvent_t */
+
+    int b200_abi_version(void);
+    char const* b200_last_error_string(void);
+    /* name of a positive (CUDA) or negative (B200_E*) code; never NULL */
+    char const* b200_error_name(int code);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Platform / device  (replaces platform/PlatformUniformCudaHipRt.hpp:41-106,
+     * dev/DevUniformCudaHipRt.hpp:109-266, acc/AccGpuUniformCudaHipRt.hpp:113-187)
+     * ------------------------------------------------------------------------------------------- */
+    typedef struct b200_device_props
+    {
+        char name[256];
+        int32_t cc_major, cc_minor;
+        int32_t multi_processor_count; /* AccDevProps::m_multiProcessorCount */
+        int32_t max_grid_dim[3]; /* x,y,z -> m_gridBlockExtentMax (reversed into alpaka's slow..fast order above) */
+        int32_t max_block_dim[3]; /* x,y,z -> m_blockThreadExtentMax */
+        int32_t max_threads_per_block; /* m_blockThreadCountMax */
+        int32_t warp_size;
+        uint64_t shared_mem_per_block; /* default limit (48 KiB), m_sharedMemSizeBytes */
+        uint64_t shared_mem_per_block_optin; /* opt-in limit (227 KiB) used internally by the native kernels */
+        uint64_t total_global_mem; /* m_globalMemSizeBytes */
+        uint64_t free_global_mem;
+        int32_t l2_cache_bytes;
+        int32_t memory_pools_supported;
+    } b200_device_props;
+
+    int b200_device_count(int* count);
+    int b200_device_props_get(int dev, b200_device_props* out);
+    int b200_device_mem_info(int dev, uint64_t* free_bytes, uint64_t* total_bytes);
+    int b200_device_sync(int dev); /* trait::CurrentThreadWaitFor<Dev> */
+    int b200_device_reset(int dev); /* trait::Reset */
+    /* cudaDeviceEnablePeerAccess all-to-all; the reference never enables it and relies on
+     * UVA staging. n_pairs_enabled may be NULL. */
+    int b200_enable_peer_all(int* n_pairs_enabled);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Queue = stream  (replaces queue/cuda_hip/QueueUniformCudaHipRt.hpp:40-242)
+     * ------------------------------------------------------------------------------------------- */
+    int b200_stream_create(int dev, b200_stream_t* out); /* cudaStreamNonBlocking, as :60-61 */
+    int b200_stream_destroy(int dev, b200_stream_t s); /* syncs first, as the queue dtor :67-76 */
+    int b200_stream_sync(b200_stream_t s); /* wait(queue) :166-177 */
+    int b200_stream_query(b200_stream_t s, int* is_empty); /* empty(queue) :145-163 */
+    typedef void (*b200_host_fn)(void* user);
+    int b200_launch_host_func(b200_stream_t s, b200_host_fn fn, void* user); /* :194-230 */
+
+    /* ---------------------------------------------------------------------------------------------
+     * Event  (replaces event/EventUniformCudaHipRt.hpp:26-260). timing=0 matches the reference
+     * (cudaEventDisableTiming, :50-52); timing=1 is an extension used by the benchmark harness.
+     * ------------------------------------------------------------------------------------------- */
+    int b200_event_create(int dev, int timing, b200_event_t* out);
+    int b200_event_destroy(b200_event_t e);
+    int b200_event_record(b200_event_t e, b200_stream_t s); /* enqueue(queue, event) */
+    int b200_event_query(b200_event_t e, int* is_complete); /* isComplete(event) */
+    int b200_event_sync(b200_event_t e); /* wait(event) */
+    int b200_stream_wait_event(b200_stream_t s, b200_event_t e); /* wait(queue, event) */
+    int b200_device_wait_event(int dev, b200_event_t e); /* wait(dev, event): all current streams of dev */
+    int b200_event_elapsed_ms(b200_event_t start, b200_event_t stop, float* ms);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Buffers  (replaces mem/buf/BufUniformCudaHipRt.hpp:205-360). allocBuf and allocAsyncBuf are both
+     * served from a per-device stream-ordered pool (cudaMallocAsync, release threshold = keep
+     * everything) instead of cudaMalloc/cudaMallocPitch; 2-D rows are padded to B200_ROW_ALIGN bytes
+     * because pools have no pitched API and the TMA stencil needs 16-byte-multiple row strides.
+     * ------------------------------------------------------------------------------------------- */
+#define B200_ROW_ALIGN 128u
+    int b200_malloc_async(int dev, b200_stream_t s, size_t bytes, void** out);
+    int b200_free_async(int dev, b200_stream_t s, void* ptr);
+    int b200_malloc_pitched_async(int dev, b200_stream_t s, size_t width_bytes, size_t height, void** out, size_t* pitch_bytes);
+    size_t b200_pitch_for_width(size_t width_bytes);
+    /* plain cudaMalloc / cudaFree: memory that must be exportable to other processes (CUDA IPC halos) */
+    int b200_malloc_device(int dev, size_t bytes, void** out);
+    int b200_free_device(int dev, void* ptr);
+    int b200_host_alloc_pinned(size_t bytes, void** out); /* allocMappedBuf :338-360 */
+    int b200_host_free_pinned(void* ptr);
+    int b200_host_register(void* ptr, size_t bytes);
+    int b200_host_unregister(void* ptr);
+    int b200_pool_stats(int dev, uint64_t* reserved_bytes, uint64_t* used_bytes);
+    int b200_pool_trim(int dev, size_t keep_bytes);
+
+    /* copies / sets  (replaces mem/buf/uniformCudaHip/Copy.hpp:32-495, Set.hpp). `dev` = device whose
+     * context issues the copy (the destination device in the reference, Copy.hpp:143). */
+    enum
+    {
+        B200_COPY_H2H = 0,
+        B200_COPY_H2D = 1,
+        B200_COPY_D2H = 2,
+        B200_COPY_D2D = 3,
+        B200_COPY_DEFAULT = 4
+    };
+    int b200_memcpy_async(int dev, void* dst, void const* src, size_t bytes, int kind, b200_stream_t s);
+    int b200_memcpy2d_async(int dev, void* dst, size_t dpitch, void const* src, size_t spitch, size_t width_bytes, size_t height, int kind, b200_stream_t s);
+    int b200_memcpy_peer_async(void* dst, int dst_dev, void const* src, int src_dev, size_t bytes, b200_stream_t s);
+    int b200_memset_async(int dev, void* dst, int byte_value, size_t bytes, b200_stream_t s);
+    int b200_memset2d_async(int dev, void* dst, size_t pitch, int byte_value, size_t width_bytes, size_t height, b200_stream_t s);
+
+    /* CUDA IPC (new; the reference is single-process). Handles are 64 opaque bytes. */
+    int b200_ipc_get_mem_handle(int dev, void* dev_ptr, unsigned char handle_out[64]);
+    int b200_ipc_open_mem_handle(int dev, unsigned char const handle[64], void** out);
+    int b200_ipc_close_mem_handle(int dev, void* ptr);
+    int b200_ipc_event_create(int dev, b200_event_t* out, unsigned char handle_out[64]);
+    int b200_ipc_event_open(int dev, unsigned char const handle[64], b200_event_t* out);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Generic kernel launch  (replaces kernel/TaskKernelGpuUniformCudaHipRt.hpp:188-366). `func` is the
+     * host address of a __global__ function registered with the SAME (shared) cudart instance.
+     * grid/block are CUDA order x,y,z.
+     * ------------------------------------------------------------------------------------------- */
+    typedef struct b200_func_attributes
+    {
+        int32_t max_threads_per_block;
+        int32_t num_regs;
+        uint64_t shared_size_bytes, const_size_bytes, local_size_bytes;
+        int32_t max_dynamic_shared_size_bytes;
+        int32_t ptx_version, binary_version;
+    } b200_func_attributes;
+    int b200_func_attributes_get(int dev, void const* func, b200_func_attributes* out);
+    int b200_launch(int dev, void const* func, uint32_t const grid[3], uint32_t const block[3], size_t dyn_smem_bytes, b200_stream_t s, void** args);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Work-division selection (host logic, no device needed)
+     * (replaces workdiv/WorkDivHelpers.hpp:133-309 subDivideGridElems and :406-549 isValidWorkDiv).
+     * Vectors are in alpaka order (index 0 = slowest dimension), `dim` entries, 1 <= dim <= 4.
+     * ------------------------------------------------------------------------------------------- */
+    typedef struct b200_acc_dev_props
+    {
+        uint64_t multi_processor_count;
+        uint64_t grid_block_extent_max[4];
+        uint64_t grid_block_count_max;
+        uint64_t block_thread_extent_max[4];
+        uint64_t block_thread_count_max;
+        uint64_t thread_elem_extent_max[4];
+        uint64_t thread_elem_count_max;
+        uint64_t shared_mem_size_bytes;
+        uint64_t global_mem_size_bytes;
+    } b200_acc_dev_props;
+    enum
+    {
+        B200_SUBDIV_EQUAL_EXTENT = 0,
+        B200_SUBDIV_CLOSE_TO_EQUAL_EXTENT = 1,
+        B200_SUBDIV_UNRESTRICTED = 2
+    };
+    int b200_acc_dev_props_get(int dev, int dim, b200_acc_dev_props* out); /* getAccDevProps<Acc>(dev) */
+    int b200_subdivide_grid_elems(
+        int dim,
+        uint64_t const* grid_elem_extent,
+        uint64_t const* thread_elem_extent,
+        b200_acc_dev_props const* props,
+        uint64_t kernel_block_thread_count_max,
+        int block_thread_must_divide_grid_thread_extent,
+        int restriction,
+        uint64_t* grid_block_extent_out,
+        uint64_t* block_thread_extent_out,
+        uint64_t* thread_elem_extent_out);
+    int b200_is_valid_work_div(
+        int dim,
+        uint64_t const* grid_block_extent,
+        uint64_t const* block_thread_extent,
+        uint64_t const* thread_elem_extent,
+        b200_acc_dev_props const* props,
+        uint64_t kernel_block_thread_count_max, /* 0 = ignore */
+        int* is_valid);
+
+    /* ---------------------------------------------------------------------------------------------
+     * BabelStream kernels (replace the functors of benchmarks/babelstream/src/babelStreamMainTest.cpp:
+     * Init :53-69, Copy :72-86, Mult :89-104, Add :107-122, Triad :125-141; Nstream is new, upstream
+     * BabelStream semantics a[i] += b[i] + scalar*c[i]). 128/256-bit vectorised grid-stride streams;
+     * FMA contraction is OFF (explicit mul then add) so results are bit-identical to the reference CPU
+     * back-end built with -ffp-contract=off. Any n >= 0 and any element-aligned pointers are accepted;
+     * the vector path needs 32-byte aligned pointers (every b200_malloc* result is).
+     * ------------------------------------------------------------------------------------------- */
+    int b200_stream_init_f64(b200_stream_t s, double* a, double* b, double* c, double init_a, uint64_t n);
+    int b200_stream_copy_f64(b200_stream_t s, double const* a, double* b, uint64_t n);
+    int b200_stream_mul_f64(b200_stream_t s, double const* a, double* b, double scalar, uint64_t n);
+    int b200_stream_add_f64(b200_stream_t s, double const* a, double const* b, double* c, uint64_t n);
+    int b200_stream_triad_f64(b200_stream_t s, double const* a, double const* b, double* c, double scalar, uint64_t n);
+    int b200_stream_nstream_f64(b200_stream_t s, double* a, double const* b, double const* c, double scalar, uint64_t n);
+    int b200_stream_init_f32(b200_stream_t s, float* a, float* b, float* c, float init_a, uint64_t n);
+    int b200_stream_copy_f32(b200_stream_t s, float const* a, float* b, uint64_t n);
+    int b200_stream_mul_f32(b200_stream_t s, float const* a, float* b, float scalar, uint64_t n);
+    int b200_stream_add_f32(b200_stream_t s, float const* a, float const* b, float* c, uint64_t n);
+    int b200_stream_triad_f32(b200_stream_t s, float const* a, float const* b, float* c, float scalar, uint64_t n);
+    int b200_stream_nstream_f32(b200_stream_t s, float* a, float const* b, float const* c, float scalar, uint64_t n);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Reductions: Dot (babelStreamMainTest.cpp:145-181 + host finish :399-405) and example/reduce
+     * (kernel.hpp:42-132 launched twice, reduce.cpp:79-98), as ONE single-pass kernel each:
+     * per-thread vectorised accumulation -> warp shuffle -> block shared memory -> per-block partial in
+     * `scratch` -> last block (atomic ticket + __threadfence) folds the partials in a fixed order and
+     * writes the scalar to out_dev[0]. Deterministic for a given device (fixed grid, fixed order).
+     * `scratch` = B200_REDUCE_SCRATCH_BYTES device bytes, zeroed ONCE by the caller (b200_memset_async);
+     * the kernel leaves it ready for the next call. One scratch per concurrently running reduction.
+     * ------------------------------------------------------------------------------------------- */
+#define B200_REDUCE_SCRATCH_BYTES 65536u
+    int b200_dot_f64(b200_stream_t s, double const* a, double const* b, uint64_t n, double* out_dev, void* scratch);
+    int b200_dot_f32(b200_stream_t s, float const* a, float const* b, uint64_t n, float* out_dev, void* scratch);
+    /* Reference-shaped Dot output: n_partials per-"block" sums whose std::reduce is the dot product, for
+     * the unmodified driver (sum[256], babelStreamMainTest.cpp:378-405). */
+    int b200_dot_partials_f64(b200_stream_t s, double const* a, double const* b, uint64_t n, double* partials_dev, uint32_t n_partials, void* scratch);
+    int b200_dot_partials_f32(b200_stream_t s, float const* a, float const* b, uint64_t n, float* partials_dev, uint32_t n_partials, void* scratch);
+    int b200_reduce_sum_u32(b200_stream_t s, uint32_t const* in, uint64_t n, uint32_t* out_dev, void* scratch);
+    int b200_reduce_sum_i32(b200_stream_t s, int32_t const* in, uint64_t n, int32_t* out_dev, void* scratch);
+    int b200_reduce_sum_u64(b200_stream_t s, uint64_t const* in, uint64_t n, uint64_t* out_dev, void* scratch);
+    int b200_reduce_sum_f32(b200_stream_t s, float const* in, uint64_t n, float* out_dev, void* scratch);
+    int b200_reduce_sum_f64(b200_stream_t s, double const* in, uint64_t n, double* out_dev, void* scratch);
+
+    /* ---------------------------------------------------------------------------------------------
+     * heatEquation2D: one fused FTCS step = StencilKernel (StencilKernel.hpp:31-89) + BoundaryKernel
+     * (BoundaryKernel.hpp:24-86) in a single persistent TMA-pipelined kernel.
+     *
+     * Field: (ny+2) x (nx+2) doubles, row-major, row pitch `pitch_bytes` (multiple of 16), base 16-byte
+     * aligned; [j][i] with j = y. Core cells 1..ny x 1..nx get
+     *   c*(1-2rX-2rY) + l*rX + r*rX + u*rY + d*rY   (left-to-right, no FMA; rX = dt/dx^2, rY = dt/dy^2),
+     * ring cells (except the four corners, which are never written, as in the reference) get
+     *   time_factor * (sx[i] + sy[j])  ==  exactSolution(i*dx, j*dy, step*dt)  bit-for-bit when the caller
+     * fills sx[i] = sin(pi*(i*dx)), sy[j] = sin(pi*(j*dy)), time_factor = exp(-pi*pi*(step*dt)) on the
+     * host with the same libm the reference CPU back-end uses.
+     *
+     * Sub-domain form for the 2-D decomposition: `edges` selects which sides of this tile are physical
+     * boundaries (get the analytic value); the other sides are ghost cells owned by a neighbour and are
+     * left untouched (filled by the halo exchange). sx/sy are indexed by LOCAL i/j.
+     * ------------------------------------------------------------------------------------------- */
+    enum
+    {
+        B200_EDGE_TOP = 1, /* j = 0 row is a physical boundary */
+        B200_EDGE_BOTTOM = 2, /* j = ny+1 */
+        B200_EDGE_LEFT = 4, /* i = 0 */
+        B200_EDGE_RIGHT = 8, /* i = nx+1 */
+        B200_EDGE_ALL = 15
+    };
+    typedef struct b200_heat2d_plan_st* b200_heat2d_plan_t;
+    /* A plan owns the TMA descriptors for a pair of ping-pong buffers and the device copies of sx/sy. */
+    int b200_heat2d_plan_create(
+        int dev,
+        double* u0,
+        double* u1,
+        size_t pitch_bytes,
+        uint32_t ny,
+        uint32_t nx,
+        double const* sx_host, /* nx+2 */
+        double const* sy_host, /* ny+2 */
+        int edges,
+        b200_heat2d_plan_t* out);
+    int b200_heat2d_plan_destroy(b200_heat2d_plan_t plan);
+    /* One step reading buffer `src_index` (0 = u0, 1 = u1) and writing the other one. */
+    int b200_heat2d_step_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor);
+    /* Restrict a step to a row/column window of OUTPUT cells [j0,j1) x [i0,i1) in padded coordinates
+     * (used to split interior / edge strips for halo overlap). */
+    int b200_heat2d_step_window_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1);
+
+    /* ---------------------------------------------------------------------------------------------
+     * Tuning / introspection (bench + profiling only)
+     * ------------------------------------------------------------------------------------------- */
+    int b200_tune_set(char const* key, int64_t value);
+    int b200_tune_get(char const* key, int64_t* value);
+    /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+    uint64_t b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
