@@ -7,11 +7,12 @@
 //     exp/sin per ring cell.
 // Here ONE persistent kernel per step:
 //   * the (TY+2) x (TX+4) input box of each 32 x 128 output tile is fetched by TMA (cp.async.bulk.tensor.2d,
-//     SASS UTMALDG) into a ring of shared-memory stages; one elected thread issues the copies and an mbarrier
-//     per stage carries the transaction count, so STAGES-1 tiles (~36 KB each) are always in flight per CTA
-//     while the 256 threads compute the current one. Out-of-range box parts are zero-filled by the TMA unit,
+//     SASS UTMALDG) into a ring of shared-memory stages; a dedicated producer warp issues the copies; a `full`
+//     mbarrier per stage carries the transaction count and an `empty` mbarrier (one arrival per consumer warp)
+//     hands the stage back, so STAGES-1 tiles (~36 KB each) stay in flight per CTA and no CTA-wide barrier sits in
+//     the tile loop. Out-of-range box parts are zero-filled by the TMA unit,
 //     so edge tiles need no address arithmetic.
-//   * each thread owns a column PAIR and walks 8 rows, keeping the 3x3 neighbourhood in registers: three
+//   * each consumer thread owns a column PAIR and walks RPT (4) rows, keeping the 3x3 neighbourhood in registers: three
 //     16-byte LDS per row (conflict-free: a warp reads 512 contiguous bytes), one 16-byte coalesced global
 //     store per row. Tiles start on even columns so every store is 16-byte aligned although core cells start at
 //     column 1.
@@ -38,10 +39,13 @@ namespace
     constexpr int BOX_Y = TY + 2;
     constexpr int BOX_BYTES = BOX_X * BOX_Y * 8; // 35904
     constexpr int STAGE_BYTES = (BOX_BYTES + 127) / 128 * 128; // TMA destination must be 128-byte aligned
-    constexpr int kThreads = 256;
-    constexpr int kRowGroups = kThreads / (TX / 2); // 4
-    constexpr int kRowsPerThread = TY / kRowGroups; // 8
     constexpr int kMaxStages = 6;
+    // Consumer threads: one per column pair x row group; RPT rows per thread (template parameter).
+    // + one producer warp that only issues TMA copies (warp-specialised, no CTA-wide barrier in the tile loop).
+    __host__ __device__ constexpr int consumerThreads(int rpt)
+    {
+        return (TX / 2) * (TY / rpt);
+    }
 
     struct HeatArgs
     {
@@ -144,11 +148,19 @@ namespace
         return false;
     }
 
-    template<int HINT>
-    __global__ void __launch_bounds__(kThreads) heatStepKernel(const __grid_constant__ CUtensorMap mapSrc, HeatArgs const A)
+    __device__ __forceinline__ void mbarArrive(uint64_t* bar)
     {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+    }
+
+    template<int HINT, int RPT>
+    __global__ void __launch_bounds__(consumerThreads(RPT) + 32) heatStepKernel(const __grid_constant__ CUtensorMap mapSrc, HeatArgs const A)
+    {
+        constexpr int kConsumers = consumerThreads(RPT);
+        constexpr int kConsumerWarps = kConsumers / 32;
         extern __shared__ __align__(128) unsigned char smem[];
         __shared__ uint64_t full[kMaxStages];
+        __shared__ uint64_t empty[kMaxStages];
 
         uint32_t const totalTiles = A.tilesX * A.tilesY;
         int const tid = threadIdx.x;
@@ -161,31 +173,43 @@ namespace
             y0 = A.j0 + ty * TY;
             x0 = A.iw0 + tx * TX;
         };
-        auto issue = [&](uint32_t t, int s)
-        {
-            uint32_t y0, x0;
-            tileOrigin(t, y0, x0);
-            mbarExpectTx(&full[s], BOX_BYTES);
-            tmaLoad2d(smem + size_t(s) * STAGE_BYTES, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 1, &full[s]);
-        };
 
-        if(tid == 0)
-        {
-            for(int s = 0; s < stages; ++s)
-                mbarInit(&full[s], 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        __syncthreads();
         if(tid == 0)
         {
             for(int s = 0; s < stages; ++s)
             {
-                uint32_t const t = blockIdx.x + uint32_t(s) * gridDim.x;
-                if(t < totalTiles)
-                    issue(t, s);
+                mbarInit(&full[s], 1);
+                mbarInit(&empty[s], kConsumerWarps);
             }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+
+        if(tid >= kConsumers)
+        {
+            // ---- producer warp: one lane streams the CTA's tiles through the stage ring
+            if(tid == kConsumers)
+            {
+                int s = 0;
+                uint32_t parity = 1; // first pass over the ring: "empty" completes immediately (preceding phase)
+                for(uint32_t t = blockIdx.x; t < totalTiles; t += gridDim.x)
+                {
+                    mbarWait(&empty[s], parity);
+                    uint32_t y0, x0;
+                    tileOrigin(t, y0, x0);
+                    mbarExpectTx(&full[s], BOX_BYTES);
+                    tmaLoad2d(smem + size_t(s) * STAGE_BYTES, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 1, &full[s]);
+                    if(++s == stages)
+                    {
+                        s = 0;
+                        parity ^= 1u;
+                    }
+                }
+            }
+            return;
         }
 
+        // ---- consumers
         int const cp = tid % (TX / 2); // column pair within the tile
         int const rg = tid / (TX / 2); // row group
         int s = 0;
@@ -198,7 +222,7 @@ namespace
 
             double const* box = reinterpret_cast<double const*>(smem + size_t(s) * STAGE_BYTES);
             // box(r, c): r = output row offset + 1, c = output col offset + 2
-            int const r0 = rg * kRowsPerThread;
+            int const r0 = rg * RPT;
             double const* p = box + size_t(r0) * BOX_X + 2 * cp; // row above the first output row, left pair
             double2 up = lds128(p + 2);
             double2 cl = lds128(p + BOX_X), cc = lds128(p + BOX_X + 2), cr = lds128(p + BOX_X + 4);
@@ -208,7 +232,7 @@ namespace
                               && x0 + TX <= A.nx + 1 && x0 >= A.i0 && x0 + TX <= A.i1;
             double* out = A.dst + size_t(y0 + r0) * A.pitchElems + gi;
 #pragma unroll
-            for(int r = 0; r < kRowsPerThread; ++r)
+            for(int r = 0; r < RPT; ++r)
             {
                 double const* q = p + size_t(r + 2) * BOX_X;
                 double2 const nl = lds128(q), nc = lds128(q + 2), nr = lds128(q + 4);
@@ -245,13 +269,10 @@ namespace
                 out += A.pitchElems;
             }
 
-            __syncthreads(); // every thread is done reading stage s
-            if(tid == 0)
-            {
-                uint32_t const tn = t + uint32_t(stages) * gridDim.x;
-                if(tn < totalTiles)
-                    issue(tn, s);
-            }
+            // this warp is done reading stage s: hand it back to the producer
+            __syncwarp();
+            if((tid & 31) == 0)
+                mbarArrive(&empty[s]);
             if(++s == stages)
             {
                 s = 0;
@@ -340,6 +361,11 @@ extern "C"
         plan->ny = ny;
         plan->nx = nx;
         plan->edges = edges;
+        int64_t const promoSel = b200::tune("heat.l2promo", 256);
+        CUtensorMapL2promotion const promo = promoSel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                             : promoSel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                             : promoSel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                               : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         for(int b = 0; b < 2; ++b)
         {
             cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(ny) + 2};
@@ -357,7 +383,7 @@ extern "C"
                 estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_NONE,
-                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                promo,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if(r != CUDA_SUCCESS)
             {
@@ -373,10 +399,15 @@ extern "C"
             e = cudaMemcpy(plan->sx, sx_host, bx, cudaMemcpyHostToDevice);
         if(e == cudaSuccess)
             e = cudaMemcpy(plan->sy, sy_host, by, cudaMemcpyHostToDevice);
-        if(e == cudaSuccess)
-            e = cudaFuncSetAttribute(heatStepKernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
-        if(e == cudaSuccess)
-            e = cudaFuncSetAttribute(heatStepKernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
+        auto optIn = [&](auto* kernel)
+        {
+            if(e == cudaSuccess)
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
+        };
+        optIn(heatStepKernel<0, 8>);
+        optIn(heatStepKernel<1, 8>);
+        optIn(heatStepKernel<0, 4>);
+        optIn(heatStepKernel<1, 4>);
         if(e != cudaSuccess)
         {
             cudaFree(plan->sx);
@@ -436,13 +467,13 @@ extern "C"
         A.sx = plan->sx;
         A.sy = plan->sy;
         A.edges = plan->edges;
-        int stages = int(b200::tune("heat.stages", 3));
+        int stages = int(b200::tune("heat.stages", 2));
         if(stages < 1)
             stages = 1;
         if(stages > kMaxStages)
             stages = kMaxStages;
         A.stages = stages;
-        int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 2));
+        int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 1));
         int const hint = int(b200::tune("heat.hint", 1));
         uint64_t const total = uint64_t(A.tilesX) * A.tilesY;
         B200_REQUIRE(total < 0xffffffffull, B200_ERANGE);
@@ -451,10 +482,25 @@ extern "C"
             grid = total;
         auto const s = reinterpret_cast<cudaStream_t>(stream);
         size_t const smemBytes = size_t(stages) * STAGE_BYTES;
-        if(hint)
-            heatStepKernel<1><<<unsigned(grid), kThreads, smemBytes, s>>>(plan->map[src_index], A);
-        else
-            heatStepKernel<0><<<unsigned(grid), kThreads, smemBytes, s>>>(plan->map[src_index], A);
+        int const rpt = int(b200::tune("heat.rpt", 4));
+        auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map[src_index], A); };
+        switch(rpt * 2 + (hint ? 1 : 0))
+        {
+        case 17:
+            launch(heatStepKernel<1, 8>, consumerThreads(8) + 32);
+            break;
+        case 16:
+            launch(heatStepKernel<0, 8>, consumerThreads(8) + 32);
+            break;
+        case 9:
+            launch(heatStepKernel<1, 4>, consumerThreads(4) + 32);
+            break;
+        case 8:
+            launch(heatStepKernel<0, 4>, consumerThreads(4) + 32);
+            break;
+        default:
+            return b200::fail(B200_EINVAL, "heat.rpt must be 4 or 8", __FILE__, __LINE__);
+        }
         B200_LAUNCH_CHECK();
         return 0;
     }

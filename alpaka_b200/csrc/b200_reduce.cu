@@ -230,7 +230,7 @@ namespace
             = reinterpret_cast<uintptr_t>(a) % 32 == 0 && (!DOT || reinterpret_cast<uintptr_t>(b) % 32 == 0);
         uint64_t const nVec = aligned ? n / N : 0;
         int const unroll = int(b200::tune(DOT ? "dot.unroll" : "reduce.unroll", DOT ? 2 : 4));
-        int const ctasPerSm = int(b200::tune(DOT ? "dot.ctas_per_sm" : "reduce.ctas_per_sm", 4));
+        int const ctasPerSm = int(b200::tune(DOT ? "dot.ctas_per_sm" : "reduce.ctas_per_sm", DOT ? 2 : 3));
         uint64_t const chunk = uint64_t(kBlock) * unroll;
         uint64_t grid = uint64_t(b200::smCount(b200::currentDevice())) * (ctasPerSm > 0 ? ctasPerSm : 4);
         uint64_t const need = (n / N + chunk - 1) / chunk;

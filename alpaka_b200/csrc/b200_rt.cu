@@ -5,6 +5,7 @@
 // cudart call sequences inside its trait specialisations (cited per function in b200.h).
 #include "b200_common.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -38,9 +39,31 @@ namespace b200
     namespace
     {
         std::mutex g_tuneMutex;
+        // Tunables: defaults live at the call sites; overrides come from b200_tune_set() or, once at load, from the
+        // environment: B200_TUNE="heat.stages=2,stream.block=256".
         std::map<std::string, int64_t>& tuneMap()
         {
-            static std::map<std::string, int64_t> m;
+            static std::map<std::string, int64_t> m = []
+            {
+                std::map<std::string, int64_t> init;
+                if(char const* env = std::getenv("B200_TUNE"))
+                {
+                    std::string s(env);
+                    size_t pos = 0;
+                    while(pos < s.size())
+                    {
+                        size_t const end = s.find(',', pos);
+                        std::string const item = s.substr(pos, end == std::string::npos ? std::string::npos : end - pos);
+                        size_t const eq = item.find('=');
+                        if(eq != std::string::npos)
+                            init[item.substr(0, eq)] = std::strtoll(item.c_str() + eq + 1, nullptr, 10);
+                        if(end == std::string::npos)
+                            break;
+                        pos = end + 1;
+                    }
+                }
+                return init;
+            }();
             return m;
         }
 
