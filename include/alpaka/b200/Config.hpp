@@ -1,0 +1,107 @@
+// include/alpaka/b200/Config.hpp -- compile-time configuration and function-attribute macros of the B200 back-end.
+//
+// API parity with the reference's include/alpaka/core/Common.hpp:29-221 (ALPAKA_FN_*), core/Unroll.hpp:16-24,
+// core/Assert.hpp, core/Debug.hpp:13-60 and version.hpp:9-11 -- same macro names and meaning, written fresh for a
+// single target: nvcc >= 12.8 compiling for sm_100a. There is exactly one accelerator here (AccGpuB200, which also
+// answers to the reference's AccGpuCudaRt / TagGpuCudaRt names); no other back-end and no CPU fallback exist, so
+// the reference's per-back-end ALPAKA_ACC_*_ENABLED matrix collapses to the two macros defined below.
+#pragma once
+
+#include <cassert>
+#include <cstddef>
+#include <cstdint>
+
+#define ALPAKA_VERSION_MAJOR 2
+#define ALPAKA_VERSION_MINOR 0
+#define ALPAKA_VERSION_PATCH 0
+#define ALPAKA_B200 1
+
+// The one enabled accelerator. Reference drivers key GPU-only code on ALPAKA_ACC_GPU_CUDA_ENABLED
+// (e.g. example/reduce/src/alpakaConfig.hpp:96) so that name is defined as well.
+#ifndef ALPAKA_ACC_GPU_B200_ENABLED
+#    define ALPAKA_ACC_GPU_B200_ENABLED
+#endif
+#ifndef ALPAKA_ACC_GPU_CUDA_ENABLED
+#    define ALPAKA_ACC_GPU_CUDA_ENABLED
+#endif
+
+#ifndef ALPAKA_DEBUG
+#    define ALPAKA_DEBUG 0
+#endif
+#define ALPAKA_DEBUG_DISABLED 0
+#define ALPAKA_DEBUG_MINIMAL 1
+#define ALPAKA_DEBUG_FULL 2
+
+#if defined(__CUDACC__)
+#    define ALPAKA_FN_ACC __device__
+#    define ALPAKA_FN_HOST_ACC __host__ __device__
+#    define ALPAKA_FN_HOST __host__
+#    define ALPAKA_FN_INLINE __forceinline__
+#    if defined(__NVCC__)
+#        define ALPAKA_NO_HOST_ACC_WARNING _Pragma("nv_exec_check_disable")
+#    else
+#        define ALPAKA_NO_HOST_ACC_WARNING
+#    endif
+#    define ALPAKA_STATIC_ACC_MEM_GLOBAL                                                                              \
+        template<typename TAccTagB200 = void>                                                                        \
+        inline __device__
+#    define ALPAKA_STATIC_ACC_MEM_CONSTANT                                                                            \
+        template<typename TAccTagB200 = void>                                                                        \
+        inline __constant__
+#else
+#    define ALPAKA_FN_ACC
+#    define ALPAKA_FN_HOST_ACC
+#    define ALPAKA_FN_HOST
+#    define ALPAKA_FN_INLINE inline __attribute__((always_inline))
+#    define ALPAKA_NO_HOST_ACC_WARNING
+#endif
+
+#define ALPAKA_FN_EXTERN extern
+
+// ALPAKA_UNROLL(n) / ALPAKA_UNROLL(): loop unrolling hint placed in front of a loop.
+#define ALPAKA_B200_PRAGMA(x) _Pragma(#x)
+#if defined(__CUDA_ARCH__)
+#    define ALPAKA_UNROLL(...) ALPAKA_B200_PRAGMA(unroll __VA_ARGS__)
+#else
+#    define ALPAKA_UNROLL(...) ALPAKA_B200_PRAGMA(GCC unroll 8)
+#endif
+
+#define ALPAKA_ASSERT(...) assert((__VA_ARGS__))
+#if defined(__CUDA_ARCH__)
+#    define ALPAKA_ASSERT_ACC(...) assert((__VA_ARGS__))
+#else
+#    define ALPAKA_ASSERT_ACC(...) assert((__VA_ARGS__))
+#endif
+#define ALPAKA_ASSERT_OFFLOAD(...) ALPAKA_ASSERT_ACC(__VA_ARGS__)
+
+#if defined(__CUDA_ARCH__)
+#    define ALPAKA_UNREACHABLE(...) __builtin_unreachable()
+#else
+#    define ALPAKA_UNREACHABLE(...) __builtin_unreachable()
+#endif
+
+#define ALPAKA_DEVICE_VOLATILE volatile
+
+// scope logging of the reference (core/Debug.hpp) is a no-op unless ALPAKA_DEBUG >= 2
+#if ALPAKA_DEBUG >= ALPAKA_DEBUG_FULL
+#    include <iostream>
+namespace alpaka::core::detail
+{
+    struct ScopeLog
+    {
+        char const* m_name;
+        explicit ScopeLog(char const* n) : m_name(n)
+        {
+            std::cout << "[+] " << m_name << std::endl;
+        }
+        ~ScopeLog()
+        {
+            std::cout << "[-] " << m_name << std::endl;
+        }
+    };
+} // namespace alpaka::core::detail
+#    define ALPAKA_DEBUG_FULL_LOG_SCOPE ::alpaka::core::detail::ScopeLog const alpakaScopeLog_(__func__)
+#else
+#    define ALPAKA_DEBUG_FULL_LOG_SCOPE
+#endif
+#define ALPAKA_DEBUG_MINIMAL_LOG_SCOPE ALPAKA_DEBUG_FULL_LOG_SCOPE
