@@ -1,0 +1,452 @@
+// include/alpaka/b200/Kernel.hpp -- kernel launch path of the B200 back-end.
+//
+// API parity with the reference's kernel/Traits.hpp:29-382 (createTaskKernel, exec, getFunctionAttributes,
+// trait::BlockSharedMemDynSizeBytes, trait::WarpSize, the trivially-copyable checks),
+// kernel/KernelFunctionAttributes.hpp:14-24, kernel/TaskKernelGpuUniformCudaHipRt.hpp:61-366 (trampoline, task,
+// Enqueue, FunctionAttributes) and workdiv/WorkDivHelpers.hpp:315-396 (KernelCfg, getValidWorkDiv).
+//
+// Two ways a task reaches the GPU:
+//   1. generic: the trampoline alpaka::b200k::run<...> (the framework's only generic __global__) builds the
+//      accelerator object and calls the user functor -- any alpaka kernel runs unchanged. The launch goes through
+//      the C ABI (b200_launch: cudaLaunchKernel by host function address on the queue's stream).
+//   2. native: trait::NativeKernel<TKernelFnObj, TAcc> can claim a functor type and forward the launch to one of the
+//      hand-written sm_100a kernels of libalpaka_b200.so (b200_stream_*, b200_dot_*, b200_heat2d_*). The library
+//      ships specialisations for the reference drivers' functors in alpaka/b200/Native.hpp (opt-in); a specialisation
+//      returns false to decline a particular launch, which then takes path 1. ALPAKA_B200_NATIVE=0 in the
+//      environment disables path 2 at run time (A/B measurement).
+#pragma once
+
+#include "Acc.hpp"
+
+#include <cstdlib>
+#include <tuple>
+#include <type_traits>
+
+namespace alpaka
+{
+    //! Kernel function attributes struct. Attributes are filled by calling the API of the accelerator using the kernel
+    //! function as an argument.
+    struct KernelFunctionAttributes
+    {
+        std::size_t constSizeBytes{0};
+        std::size_t localSizeBytes{0};
+        std::size_t sharedSizeBytes{0};
+        int maxDynamicSharedSizeBytes{0};
+        int numRegs{0};
+        int asmVersion{0}; //!< PTX version the kernel was compiled for
+        int maxThreadsPerBlock{0};
+    };
+
+    namespace trait
+    {
+        //! The trait for getting the size of the block shared dynamic memory of a kernel.
+        //! The default implementation returns 0; specialise per (kernel functor, accelerator).
+        template<typename TKernelFnObj, typename TAcc, typename TSfinae = void>
+        struct BlockSharedMemDynSizeBytes
+        {
+            template<typename TDim, typename... TArgs>
+            ALPAKA_FN_HOST_ACC static auto getBlockSharedMemDynSizeBytes(
+                TKernelFnObj const& /*kernelFnObj*/,
+                Vec<TDim, Idx<TAcc>> const& /*blockThreadExtent*/,
+                Vec<TDim, Idx<TAcc>> const& /*threadElemExtent*/,
+                TArgs const&... /*args*/) -> std::size_t
+            {
+                return 0u;
+            }
+        };
+
+        //! The trait for getting the warp size required by a kernel (0 = any). The B200 only has 32-wide warps.
+        template<typename TKernelFnObj, typename TAcc, typename TSfinae = void>
+        struct WarpSize : std::integral_constant<std::uint32_t, 0>
+        {
+        };
+
+        //! Hook: lets a library claim a kernel functor type for a hand-written implementation.
+        //! A specialisation defines `available = true` and
+        //!   template<typename TQueue, typename TWorkDiv, typename... TArgs>
+        //!   static bool launch(TQueue&, TWorkDiv const&, TKernelFnObj const&, TArgs const&...);
+        //! returning false if it declines this particular launch.
+        template<typename TKernelFnObj, typename TAcc, typename TSfinae = void>
+        struct NativeKernel
+        {
+            static constexpr bool available = false;
+        };
+
+        template<typename TAcc, typename TDev, typename TKernelFnObj, typename... TArgs>
+        struct FunctionAttributes;
+
+        template<typename TAcc, typename TWorkDiv, typename TKernelFnObj, typename... TArgs>
+        struct CreateTaskKernel;
+    } // namespace trait
+
+    template<typename TKernelFnObj, typename TAcc>
+    inline constexpr std::uint32_t warpSize = trait::WarpSize<TKernelFnObj, TAcc>::value;
+
+    //! \return The size of the shared memory allocated for a block in bytes.
+    template<typename TAcc, typename TKernelFnObj, typename TDim, typename... TArgs>
+    ALPAKA_FN_HOST_ACC auto getBlockSharedMemDynSizeBytes(
+        TKernelFnObj const& kernelFnObj,
+        Vec<TDim, Idx<TAcc>> const& blockThreadExtent,
+        Vec<TDim, Idx<TAcc>> const& threadElemExtent,
+        TArgs const&... args) -> std::size_t
+    {
+        return trait::BlockSharedMemDynSizeBytes<TKernelFnObj, TAcc>::getBlockSharedMemDynSizeBytes(
+            kernelFnObj,
+            blockThreadExtent,
+            threadElemExtent,
+            args...);
+    }
+
+    namespace b200
+    {
+        //! ALPAKA_B200_NATIVE=0 routes every launch through the generic trampoline
+        inline auto nativeKernelsEnabled() -> bool
+        {
+            static bool const enabled = []
+            {
+                char const* e = std::getenv("ALPAKA_B200_NATIVE");
+                return !(e != nullptr && e[0] == '0');
+            }();
+            return enabled;
+        }
+    } // namespace b200
+
+#if defined(__CUDACC__)
+    // short namespace: keeps the mangled kernel name in profiler output readable
+    // (same consideration as the reference, kernel/TaskKernelGpuUniformCudaHipRt.hpp:58-60)
+    namespace b200k
+    {
+        //! The generic kernel trampoline: builds the accelerator and calls the user's functor.
+        template<typename TKernelFnObj, typename TAcc, typename TDim, typename TIdx, typename... TArgs>
+        __global__ void run(Vec<TDim, TIdx> const threadElemExtent, TKernelFnObj const kernelFnObj, TArgs... args)
+        {
+            TAcc const acc(threadElemExtent);
+            kernelFnObj(acc, args...);
+        }
+    } // namespace b200k
+#endif
+
+    namespace detail
+    {
+        template<typename T>
+        struct IsKernelArgumentTriviallyCopyable
+        {
+#if defined(__NVCC__) && defined(__CUDACC_EXTENDED_LAMBDA__)
+            // extended lambdas are seen by the host pass through a placeholder closure type
+            static constexpr bool value = std::is_trivially_copyable_v<T> || __nv_is_extended_device_lambda_closure_type(T)
+                                          || __nv_is_extended_host_device_lambda_closure_type(T);
+#else
+            static constexpr bool value = std::is_trivially_copyable_v<T>;
+#endif
+        };
+    } // namespace detail
+    //! customisation point: declare a kernel argument type copyable by memcpy although the language cannot prove it
+    template<typename T, typename = void>
+    struct IsKernelArgumentTriviallyCopyable : detail::IsKernelArgumentTriviallyCopyable<T>
+    {
+    };
+    template<typename T>
+    inline constexpr bool isKernelArgumentTriviallyCopyable = IsKernelArgumentTriviallyCopyable<T>::value;
+    template<typename T>
+    inline constexpr bool isKernelTriviallyCopyable = IsKernelArgumentTriviallyCopyable<T>::value;
+
+    //! The kernel execution task of the B200 back-end: work division + functor + arguments, all held by value.
+    template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+    class TaskKernelB200 final : public WorkDivMembers<TDim, TIdx>
+    {
+    public:
+        template<typename TWorkDiv>
+        TaskKernelB200(TWorkDiv&& workDiv, TKernelFnObj const& kernelFnObj, TArgs&&... args)
+            : WorkDivMembers<TDim, TIdx>(std::forward<TWorkDiv>(workDiv))
+            , m_kernelFnObj(kernelFnObj)
+            , m_args(std::forward<TArgs>(args)...)
+        {
+            static_assert(
+                Dim<std::decay_t<TWorkDiv>>::value == TDim::value,
+                "The work division and the execution task have to be of the same dimensionality!");
+        }
+
+        TKernelFnObj m_kernelFnObj;
+        std::tuple<std::decay_t<TArgs>...> m_args;
+    };
+
+    namespace trait
+    {
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct AccType<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>>
+        {
+            using type = TAcc;
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct DevType<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>>
+        {
+            using type = DevB200;
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct DimType<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>>
+        {
+            using type = TDim;
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct IdxType<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>>
+        {
+            using type = TIdx;
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct GetWorkDiv<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>, origin::Grid, unit::Blocks>
+        {
+            static auto getWorkDiv(WorkDivMembers<TDim, TIdx> const& w) -> Vec<TDim, TIdx>
+            {
+                return w.m_gridBlockExtent;
+            }
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct GetWorkDiv<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>, origin::Block, unit::Threads>
+        {
+            static auto getWorkDiv(WorkDivMembers<TDim, TIdx> const& w) -> Vec<TDim, TIdx>
+            {
+                return w.m_blockThreadExtent;
+            }
+        };
+        template<typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct GetWorkDiv<TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>, origin::Thread, unit::Elems>
+        {
+            static auto getWorkDiv(WorkDivMembers<TDim, TIdx> const& w) -> Vec<TDim, TIdx>
+            {
+                return w.m_threadElemExtent;
+            }
+        };
+
+        template<typename TApi, typename TDim, typename TIdx, typename TWorkDiv, typename TKernelFnObj, typename... TArgs>
+        struct CreateTaskKernel<AccGpuUniformCudaHipRt<TApi, TDim, TIdx>, TWorkDiv, TKernelFnObj, TArgs...>
+        {
+            static auto createTaskKernel(TWorkDiv const& workDiv, TKernelFnObj const& kernelFnObj, TArgs&&... args)
+            {
+                return TaskKernelB200<AccGpuUniformCudaHipRt<TApi, TDim, TIdx>, TDim, TIdx, TKernelFnObj, TArgs...>(
+                    workDiv,
+                    kernelFnObj,
+                    std::forward<TArgs>(args)...);
+            }
+        };
+
+#if defined(__CUDACC__)
+        template<typename TApi, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct FunctionAttributes<AccGpuUniformCudaHipRt<TApi, TDim, TIdx>, DevB200, TKernelFnObj, TArgs...>
+        {
+            static auto getFunctionAttributes(DevB200 const& dev, TKernelFnObj const&, TArgs&&...) -> KernelFunctionAttributes
+            {
+                using TAcc = AccGpuUniformCudaHipRt<TApi, TDim, TIdx>;
+                auto const kernel = b200k::run<TKernelFnObj, TAcc, TDim, TIdx, std::decay_t<TArgs>...>;
+                b200_func_attributes a{};
+                b200::check(b200_func_attributes_get(dev.getNativeHandle(), reinterpret_cast<void const*>(kernel), &a));
+                KernelFunctionAttributes r;
+                r.constSizeBytes = a.const_size_bytes;
+                r.localSizeBytes = a.local_size_bytes;
+                r.sharedSizeBytes = a.shared_size_bytes;
+                r.maxDynamicSharedSizeBytes = a.max_dynamic_shared_size_bytes;
+                r.numRegs = a.num_regs;
+                r.asmVersion = a.ptx_version;
+                r.maxThreadsPerBlock = a.max_threads_per_block;
+                return r;
+            }
+        };
+
+        template<typename TProperty, typename TAcc, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        struct Enqueue<QueueB200<TProperty>, TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>>
+        {
+            using Task = TaskKernelB200<TAcc, TDim, TIdx, TKernelFnObj, TArgs...>;
+
+            static void enqueue(QueueB200<TProperty>& queue, Task const& task)
+            {
+                // 1. a hand-written kernel may claim this functor
+                if constexpr(NativeKernel<TKernelFnObj, TAcc>::available)
+                {
+                    if(b200::nativeKernelsEnabled())
+                    {
+                        bool const handled = std::apply(
+                            [&](auto const&... args)
+                            {
+                                return NativeKernel<TKernelFnObj, TAcc>::launch(
+                                    queue,
+                                    static_cast<WorkDivMembers<TDim, TIdx> const&>(task),
+                                    task.m_kernelFnObj,
+                                    args...);
+                            },
+                            task.m_args);
+                        if(handled)
+                        {
+                            queue.afterEnqueue();
+                            return;
+                        }
+                    }
+                }
+
+                // 2. generic trampoline
+                auto const gridBlockExtent = getWorkDiv<Grid, Blocks>(task);
+                auto const blockThreadExtent = getWorkDiv<Block, Threads>(task);
+                auto threadElemExtent = getWorkDiv<Thread, Elems>(task);
+
+                uint32_t grid[3] = {1u, 1u, 1u};
+                uint32_t block[3] = {1u, 1u, 1u};
+                for(std::size_t d = 0; d < TDim::value; ++d)
+                {
+                    // alpaka's fastest (last) dimension is CUDA x
+                    grid[d] = static_cast<uint32_t>(gridBlockExtent[TDim::value - 1u - d]);
+                    block[d] = static_cast<uint32_t>(blockThreadExtent[TDim::value - 1u - d]);
+                }
+
+#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
+                if(!isValidWorkDiv<TAcc>(task, getDev(queue)))
+                    throw std::runtime_error(
+                        "The given work division is not valid or not supported by the device of type "
+                        + getAccName<TAcc>() + "!");
+#    endif
+                std::size_t const dynSmemBytes = std::apply(
+                    [&](auto const&... args)
+                    {
+                        return getBlockSharedMemDynSizeBytes<TAcc>(task.m_kernelFnObj, blockThreadExtent, threadElemExtent, args...);
+                    },
+                    task.m_args);
+
+                auto const kernel = b200k::run<TKernelFnObj, TAcc, TDim, TIdx, std::decay_t<TArgs>...>;
+
+                // cudaLaunchKernel wants one pointer per kernel parameter, in order
+                constexpr std::size_t nArgs = sizeof...(TArgs);
+                void* argv[2u + nArgs];
+                argv[0] = const_cast<void*>(static_cast<void const*>(&threadElemExtent));
+                argv[1] = const_cast<void*>(static_cast<void const*>(&task.m_kernelFnObj));
+                std::size_t i = 2u;
+                std::apply(
+                    [&](auto const&... args) { ((argv[i++] = const_cast<void*>(static_cast<void const*>(&args))), ...); },
+                    task.m_args);
+
+                b200::check(b200_launch(
+                    getDev(queue).getNativeHandle(),
+                    reinterpret_cast<void const*>(kernel),
+                    grid,
+                    block,
+                    dynSmemBytes,
+                    queue.getNativeHandle(),
+                    argv));
+#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
+                // debug builds surface asynchronous launch failures at the launch site, like the reference
+                b200::check(b200_stream_sync(queue.getNativeHandle()));
+#    endif
+                queue.afterEnqueue();
+            }
+        };
+#endif // __CUDACC__
+    } // namespace trait
+
+    //! Creates a kernel execution task.
+    //! \tparam TAcc The accelerator type.
+    //! \param workDiv The index domain work division.
+    //! \param kernelFnObj The kernel function object which should be executed.
+    //! \param args The kernel invocation arguments.
+    template<typename TAcc, typename TWorkDiv, typename TKernelFnObj, typename... TArgs>
+    [[nodiscard]] auto createTaskKernel(TWorkDiv const& workDiv, TKernelFnObj const& kernelFnObj, TArgs&&... args)
+    {
+        static_assert(
+            isKernelTriviallyCopyable<TKernelFnObj>,
+            "Kernels must be trivially copyable or specialize trait::IsKernelTriviallyCopyable<>!");
+        static_assert(
+            (isKernelArgumentTriviallyCopyable<std::decay_t<TArgs>> && ...),
+            "The kernel arguments must be trivially copyable or specialize trait::IsKernelArgumentTriviallyCopyable<>!");
+        static_assert(
+            Dim<std::decay_t<TWorkDiv>>::value == Dim<TAcc>::value,
+            "The dimensions of TAcc and TWorkDiv have to be identical!");
+        static_assert(
+            std::is_same_v<Idx<std::decay_t<TWorkDiv>>, Idx<TAcc>>,
+            "The idx type of TAcc and the idx type of TWorkDiv have to be identical!");
+        return trait::CreateTaskKernel<TAcc, TWorkDiv, TKernelFnObj, TArgs...>::createTaskKernel(
+            workDiv,
+            kernelFnObj,
+            std::forward<TArgs>(args)...);
+    }
+
+    //! Executes the given kernel in the given queue.
+    template<typename TAcc, typename TQueue, typename TWorkDiv, typename TKernelFnObj, typename... TArgs>
+    auto exec(TQueue& queue, TWorkDiv const& workDiv, TKernelFnObj const& kernelFnObj, TArgs&&... args) -> void
+    {
+        enqueue(queue, createTaskKernel<TAcc>(workDiv, kernelFnObj, std::forward<TArgs>(args)...));
+    }
+
+    //! \return The kernel function attributes (registers, shared memory, maximum threads per block) of the generic
+    //! launch of `kernelFnObj(acc, args...)` on the given device.
+    template<typename TAcc, typename TDev, typename TKernelFnObj, typename... TArgs>
+    [[nodiscard]] auto getFunctionAttributes(TDev const& dev, TKernelFnObj const& kernelFnObj, TArgs&&... args)
+        -> KernelFunctionAttributes
+    {
+        return trait::FunctionAttributes<TAcc, TDev, TKernelFnObj, TArgs...>::getFunctionAttributes(
+            dev,
+            kernelFnObj,
+            std::forward<TArgs>(args)...);
+    }
+
+    //! Kernel start configuration to determine a valid work division.
+    template<
+        typename TAcc,
+        typename TGridElemExtent = Vec<Dim<TAcc>, Idx<TAcc>>,
+        typename TThreadElemExtent = Vec<Dim<TAcc>, Idx<TAcc>>>
+    struct KernelCfg
+    {
+        //! The full extent of elements in the grid.
+        TGridElemExtent const gridElemExtent = Vec<Dim<TAcc>, Idx<TAcc>>::ones();
+        //! The number of elements computed per thread.
+        TThreadElemExtent const threadElemExtent = Vec<Dim<TAcc>, Idx<TAcc>>::ones();
+        //! If true, the grid thread extent is a multiple of the block thread extent in every dimension.
+        bool blockThreadMustDivideGridThreadExtent = true;
+        //! The grid block extent subdivision restrictions.
+        GridBlockExtentSubDivRestrictions gridBlockExtentSubDivRestrictions = GridBlockExtentSubDivRestrictions::Unrestricted;
+
+        static_assert(
+            Dim<TGridElemExtent>::value == Dim<TAcc>::value && Dim<TThreadElemExtent>::value == Dim<TAcc>::value,
+            "The dimension of Acc and of the extents have to be identical!");
+        static_assert(
+            std::is_same_v<Idx<TGridElemExtent>, Idx<TAcc>> && std::is_same_v<Idx<TThreadElemExtent>, Idx<TAcc>>,
+            "The idx type of Acc and of the extents have to be identical!");
+    };
+
+    //! \return A work division valid for the accelerator, the device and the kernel
+    //! (block size limited by the kernel's registers/shared memory).
+    template<typename TAcc, typename TDev, typename TGridElemExtent, typename TThreadElemExtent, typename TKernelFnObj, typename... TArgs>
+    [[nodiscard]] auto getValidWorkDiv(
+        KernelCfg<TAcc, TGridElemExtent, TThreadElemExtent> const& kernelCfg,
+        TDev const& dev,
+        TKernelFnObj const& kernelFnObj,
+        TArgs&&... args) -> WorkDivMembers<Dim<TAcc>, Idx<TAcc>>
+    {
+        using I = Idx<TAcc>;
+        if constexpr(Dim<TAcc>::value == 0u)
+        {
+            auto const zero = Vec<DimInt<0u>, I>{};
+            return WorkDivMembers<DimInt<0u>, I>{zero, zero, zero};
+        }
+        else
+        {
+            auto const attrs = getFunctionAttributes<TAcc>(dev, kernelFnObj, std::forward<TArgs>(args)...);
+            return subDivideGridElems(
+                getExtents(kernelCfg.gridElemExtent),
+                getExtents(kernelCfg.threadElemExtent),
+                getAccDevProps<TAcc>(dev),
+                static_cast<I>(attrs.maxThreadsPerBlock),
+                kernelCfg.blockThreadMustDivideGridThreadExtent,
+                kernelCfg.gridBlockExtentSubDivRestrictions);
+        }
+    }
+
+    //! Checks if the work division is supported by the accelerator on the device for the given kernel.
+    template<typename TAcc, typename TWorkDiv, typename TDev, typename TKernelFnObj, typename... TArgs>
+    [[nodiscard]] auto isValidWorkDiv(TWorkDiv const& workDiv, TDev const& dev, TKernelFnObj const& kernelFnObj, TArgs&&... args)
+        -> bool
+    {
+        auto const attrs = getFunctionAttributes<TAcc>(dev, kernelFnObj, std::forward<TArgs>(args)...);
+        return isValidWorkDiv(workDiv, getAccDevProps<TAcc>(dev), static_cast<std::size_t>(attrs.maxThreadsPerBlock));
+    }
+    //! Checks if the work division is supported by the accelerator on the device.
+    template<typename TAcc, typename TWorkDiv, typename TDev>
+    [[nodiscard]] auto isValidWorkDiv(TWorkDiv const& workDiv, TDev const& dev) -> bool
+    {
+        return isValidWorkDiv(workDiv, getAccDevProps<TAcc>(dev));
+    }
+} // namespace alpaka

@@ -665,6 +665,7 @@ namespace alpaka
         };
     } // namespace trait
 
+    ALPAKA_NO_HOST_ACC_WARNING
     template<typename T>
     [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto getExtents(T const& object) -> Vec<Dim<T>, Idx<T>>
     {
@@ -680,6 +681,7 @@ namespace alpaka
     {
         return subVecEnd<TSubDim>(getExtents(object));
     }
+    ALPAKA_NO_HOST_ACC_WARNING
     template<typename T>
     [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto getOffsets(T const& object) -> Vec<Dim<T>, Idx<T>>
     {
