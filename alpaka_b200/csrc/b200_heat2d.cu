@@ -281,6 +281,45 @@ namespace
         }
     }
 
+
+    // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
+    // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
+    __global__ void __launch_bounds__(256) heatBoundaryKernel(HeatArgs const A)
+    {
+        uint64_t const t = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+        uint64_t const nx = A.nx, ny = A.ny;
+        if(t >= 2 * nx + 2 * ny)
+            return;
+        uint32_t j, i;
+        int side;
+        if(t < nx)
+        {
+            j = 0;
+            i = uint32_t(t) + 1;
+            side = B200_EDGE_TOP;
+        }
+        else if(t < 2 * nx)
+        {
+            j = A.ny + 1;
+            i = uint32_t(t - nx) + 1;
+            side = B200_EDGE_BOTTOM;
+        }
+        else if(t < 2 * nx + ny)
+        {
+            j = uint32_t(t - 2 * nx) + 1;
+            i = 0;
+            side = B200_EDGE_LEFT;
+        }
+        else
+        {
+            j = uint32_t(t - 2 * nx - ny) + 1;
+            i = A.nx + 1;
+            side = B200_EDGE_RIGHT;
+        }
+        if(A.edges & side)
+            A.dst[size_t(j) * A.pitchElems + i] = __dmul_rn(A.tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
+    }
+
     // ---- host side
     using EncodeTiledFn = CUresult (*)(
         CUtensorMap*,
@@ -501,6 +540,25 @@ extern "C"
         default:
             return b200::fail(B200_EINVAL, "heat.rpt must be 4 or 8", __FILE__, __LINE__);
         }
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int b200_heat2d_boundary_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int dst_index, double time_factor)
+    {
+        B200_REQUIRE(plan && (dst_index == 0 || dst_index == 1), B200_EINVAL);
+        B200_CUDA(cudaSetDevice(plan->dev));
+        HeatArgs A{};
+        A.dst = plan->u[dst_index];
+        A.pitchElems = plan->pitchBytes / 8;
+        A.ny = plan->ny;
+        A.nx = plan->nx;
+        A.tf = time_factor;
+        A.sx = plan->sx;
+        A.sy = plan->sy;
+        A.edges = plan->edges;
+        uint64_t const cells = 2 * (uint64_t(plan->nx) + plan->ny);
+        heatBoundaryKernel<<<unsigned((cells + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(A);
         B200_LAUNCH_CHECK();
         return 0;
     }

@@ -1,0 +1,177 @@
+// examples/heatEquation2D/heat2d_b200.cpp -- heatEquation2D on the B200 back-end with run-time sizes.
+//
+// The reference's StencilKernel, BoundaryKernel, exactSolution/validateSolution/initalizeBuffer and getElementPtr are
+// used UNMODIFIED (included from example/heatEquation2D/src of the reference tree through -I; nothing is copied).
+// Only the driver is replaced, because the shipped one fixes 64x64 nodes, 4000 steps and tMax = 0.1 at compile time
+// (example/heatEquation2D/src/heatEquation2D.cpp:54-59). The host sequence follows heatEquation2D.cpp:34-203.
+//
+//   --mode=functors   per step: exec(StencilKernel), exec(BoundaryKernel), swap -- the reference's two launches
+//                     (native TMA stencil + ring kernel when the functors are recognised, generic trampoline with
+//                     ALPAKA_B200_NATIVE=0)
+//   --mode=fused      per step: one launch of the fused native kernel (alpaka::b200::Heat2DStepper)
+//   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
+//   --output=<file>   dump the final (ny+2) x (nx+2) field, unpadded, for the parity tests
+#include "../common/cli.hpp"
+#include "BoundaryKernel.hpp" // reference: example/heatEquation2D/src
+#include "StencilKernel.hpp" // reference
+#include "analyticalSolution.hpp" // reference
+
+#include <alpaka/alpaka.hpp>
+
+#include <chrono>
+#include <iostream>
+#include <sstream>
+
+auto main(int argc, char** argv) -> int
+{
+    try
+    {
+        cli::Args const args(argc, argv);
+        using Dim = alpaka::DimInt<2u>;
+        using Idx = uint32_t;
+        using Acc = alpaka::AccGpuB200<Dim, Idx>;
+        using Vec2 = alpaka::Vec<Dim, Idx>;
+
+        auto const ny = static_cast<Idx>(args.u64("ny", 64));
+        auto const nx = static_cast<Idx>(args.u64("nx", 64));
+        auto const numTimeSteps = static_cast<uint32_t>(args.u64("steps", 4000));
+        std::string const mode = args.str("mode", "functors");
+
+        auto const devHost = alpaka::getDevByIdx(alpaka::PlatformCpu{}, 0);
+        auto const devAcc = alpaka::getDevByIdx(alpaka::Platform<Acc>{}, 0);
+
+        Vec2 const numNodes{ny, nx};
+        Vec2 const haloSize{2u, 2u};
+        Vec2 const extent = numNodes + haloSize;
+
+        double const dx = 1.0 / static_cast<double>(extent[1] - 1);
+        double const dy = 1.0 / static_cast<double>(extent[0] - 1);
+        double const dt = args.has("dt") ? args.f64("dt", 0.0) : args.f64("dt-factor", 0.2) * std::min(dx * dx, dy * dy);
+        double const tMax = dt * numTimeSteps;
+
+        // the reference's stability check (heatEquation2D.cpp:66-73)
+        double const r = 2 * dt / ((dx * dx * dy * dy) / (dx * dx + dy * dy));
+        if(r > 1.)
+        {
+            std::cerr << "Stability condition check failed: dt/min(dx^2,dy^2) = " << r << ", it is required to be <= 0.5\n";
+            return EXIT_FAILURE;
+        }
+
+        auto uBufHost = alpaka::allocBuf<double, Idx>(devHost, extent);
+        auto uCurrBufAcc = alpaka::allocBuf<double, Idx>(devAcc, extent);
+        auto uNextBufAcc = alpaka::allocBuf<double, Idx>(devAcc, extent);
+        auto const pitchCurrAcc{alpaka::getPitchesInBytes(uCurrBufAcc)};
+        auto const pitchNextAcc{alpaka::getPitchesInBytes(uNextBufAcc)};
+
+        initalizeBuffer(uBufHost, dx, dy);
+
+        using QueueAcc = alpaka::Queue<Acc, alpaka::NonBlocking>;
+        QueueAcc computeQueue{devAcc};
+        alpaka::memcpy(computeQueue, uCurrBufAcc, uBufHost);
+        // the corners of the field are never written by either kernel; start both buffers from the same values so the
+        // final dump is fully defined (the reference leaves uNext's corners uninitialised; they are never read)
+        alpaka::memcpy(computeQueue, uNextBufAcc, uBufHost);
+        alpaka::wait(computeQueue);
+
+        constexpr Idx xSize = 16u;
+        constexpr Idx ySize = 16u;
+        constexpr Idx halo = 2u;
+        Vec2 const chunkSize{ySize, xSize};
+        constexpr auto sharedMemSize = (ySize + halo) * (xSize + halo);
+        Vec2 const elemPerThread{1u, 1u};
+
+        auto const t0 = std::chrono::high_resolution_clock::now();
+        std::size_t launches = 0;
+        if(mode == "functors")
+        {
+            if(ny % chunkSize[0] != 0 || nx % chunkSize[1] != 0)
+            {
+                std::cerr << "Domain must be divisible by chunk size (16)\n"; // heatEquation2D.cpp:114-116
+                return EXIT_FAILURE;
+            }
+            Vec2 const numChunks{alpaka::core::divCeil(numNodes[0], chunkSize[0]), alpaka::core::divCeil(numNodes[1], chunkSize[1])};
+            StencilKernel<sharedMemSize> stencilKernel;
+            BoundaryKernel boundaryKernel;
+            auto const attrs = alpaka::getFunctionAttributes<Acc>(
+                devAcc,
+                stencilKernel,
+                uCurrBufAcc.data(),
+                uNextBufAcc.data(),
+                chunkSize,
+                pitchCurrAcc,
+                pitchNextAcc,
+                dx,
+                dy,
+                dt);
+            auto const maxThreadsPerBlock = static_cast<Idx>(attrs.maxThreadsPerBlock);
+            auto const threadsPerBlock = maxThreadsPerBlock < chunkSize.prod() ? Vec2{maxThreadsPerBlock, 1u} : chunkSize;
+            alpaka::WorkDivMembers<Dim, Idx> workDiv{numChunks, threadsPerBlock, elemPerThread};
+
+            for(uint32_t step = 1; step <= numTimeSteps; ++step)
+            {
+                alpaka::exec<Acc>(
+                    computeQueue,
+                    workDiv,
+                    stencilKernel,
+                    uCurrBufAcc.data(),
+                    uNextBufAcc.data(),
+                    chunkSize,
+                    pitchCurrAcc,
+                    pitchNextAcc,
+                    dx,
+                    dy,
+                    dt);
+                alpaka::exec<Acc>(computeQueue, workDiv, boundaryKernel, uNextBufAcc.data(), chunkSize, pitchNextAcc, step, dx, dy, dt);
+                std::swap(uNextBufAcc, uCurrBufAcc);
+                launches += 2;
+            }
+        }
+        else if(mode == "fused")
+        {
+            alpaka::b200::Heat2DStepper stepper(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
+            for(uint32_t step = 1; step <= numTimeSteps; ++step)
+            {
+                stepper.step(computeQueue);
+                ++launches;
+            }
+            alpaka::wait(computeQueue);
+            if(stepper.currentIndex() == 1)
+                std::swap(uNextBufAcc, uCurrBufAcc);
+        }
+        else
+        {
+            std::cerr << "unknown --mode " << mode << std::endl;
+            return 2;
+        }
+        alpaka::wait(computeQueue);
+        auto const t1 = std::chrono::high_resolution_clock::now();
+        double const seconds = std::chrono::duration<double>(t1 - t0).count();
+
+        alpaka::memcpy(computeQueue, uBufHost, uCurrBufAcc);
+        alpaka::wait(computeQueue);
+
+        auto const [resultIsCorrect, maxError] = validateSolution(uBufHost, extent, dx, dy, tMax);
+        if(args.has("output"))
+            cli::writeFile(args.str("output"), uBufHost.data(), sizeof(double) * std::size_t(extent[0]) * extent[1]);
+
+        double const gbs = 16.0 * double(ny) * double(nx) * numTimeSteps * 1e-9 / seconds;
+        std::ostringstream json;
+        json << "{\"driver\": \"heat2d_b200\", \"mode\": \"" << mode << "\", \"ny\": " << ny << ", \"nx\": " << nx
+             << ", \"steps\": " << numTimeSteps << ", \"native\": " << (alpaka::b200::nativeKernelsEnabled() ? "true" : "false")
+             << ", \"launches\": " << launches << ", \"seconds\": " << seconds << ", \"ms_per_step\": " << seconds * 1e3 / numTimeSteps
+             << ", \"gbs\": " << gbs << ", \"max_error\": " << maxError << "}";
+        std::cout << json.str() << std::endl;
+        if(resultIsCorrect)
+        {
+            std::cout << "Execution results correct!" << std::endl;
+            return EXIT_SUCCESS;
+        }
+        std::cout << "Execution results incorrect: Max error = " << maxError << " (the grid resolution may be too low)" << std::endl;
+        return EXIT_FAILURE;
+    }
+    catch(std::exception const& e)
+    {
+        std::cerr << "heat2d_b200: " << e.what() << std::endl;
+        return 2;
+    }
+}

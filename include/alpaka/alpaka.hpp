@@ -20,3 +20,4 @@
 #include "b200/Acc.hpp"
 #include "b200/Kernel.hpp"
 #include "b200/Native.hpp"
+#include "b200/Heat2D.hpp"

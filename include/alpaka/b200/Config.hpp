@@ -60,7 +60,7 @@
 
 // ALPAKA_UNROLL(n) / ALPAKA_UNROLL(): loop unrolling hint placed in front of a loop.
 #define ALPAKA_B200_PRAGMA(x) _Pragma(#x)
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 #    define ALPAKA_UNROLL(...) ALPAKA_B200_PRAGMA(unroll __VA_ARGS__)
 #else
 #    define ALPAKA_UNROLL(...) ALPAKA_B200_PRAGMA(GCC unroll 8)

@@ -99,6 +99,17 @@ namespace alpaka
 
     namespace b200
     {
+        //! The "+" reduction functor. A plain struct instead of a lambda so that libraries can recognise it
+        //! (alpaka/b200/Native.hpp routes ReduceKernel<.., Sum<T>> to the native single-pass reduction).
+        template<typename T>
+        struct Sum
+        {
+            ALPAKA_FN_HOST_ACC constexpr auto operator()(T const& a, T const& b) const -> T
+            {
+                return a + b;
+            }
+        };
+
         //! ALPAKA_B200_NATIVE=0 routes every launch through the generic trampoline
         inline auto nativeKernelsEnabled() -> bool
         {
@@ -124,6 +135,65 @@ namespace alpaka
             kernelFnObj(acc, args...);
         }
     } // namespace b200k
+#endif
+
+#if defined(__CUDACC__)
+    namespace b200
+    {
+        //! Launches `kernelFnObj(acc, args...)` through the generic trampoline on the queue's stream (no
+        //! blocking-queue synchronisation; the caller does that). Also what a NativeKernel specialisation calls to
+        //! cross-check itself against the user's functor.
+        template<typename TAcc, typename TQueue, typename TDim, typename TIdx, typename TKernelFnObj, typename... TArgs>
+        void launchGeneric(
+            TQueue& queue,
+            WorkDivMembers<TDim, TIdx> const& workDiv,
+            TKernelFnObj const& kernelFnObj,
+            TArgs const&... args)
+        {
+            auto const gridBlockExtent = workDiv.m_gridBlockExtent;
+            auto const blockThreadExtent = workDiv.m_blockThreadExtent;
+            auto threadElemExtent = workDiv.m_threadElemExtent;
+
+            uint32_t grid[3] = {1u, 1u, 1u};
+            uint32_t block[3] = {1u, 1u, 1u};
+            for(std::size_t d = 0; d < TDim::value; ++d)
+            {
+                // alpaka's fastest (last) dimension is CUDA x
+                grid[d] = static_cast<uint32_t>(gridBlockExtent[TDim::value - 1u - d]);
+                block[d] = static_cast<uint32_t>(blockThreadExtent[TDim::value - 1u - d]);
+            }
+
+#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
+            if(!isValidWorkDiv(workDiv, getAccDevProps<TAcc>(getDev(queue))))
+                throw std::runtime_error(
+                    "The given work division is not valid or not supported by the device of type " + getAccName<TAcc>()
+                    + "!");
+#    endif
+            std::size_t const dynSmemBytes
+                = getBlockSharedMemDynSizeBytes<TAcc>(kernelFnObj, blockThreadExtent, threadElemExtent, args...);
+
+            auto const kernel = b200k::run<TKernelFnObj, TAcc, TDim, TIdx, TArgs...>;
+
+            // cudaLaunchKernel wants one pointer per kernel parameter, in order
+            void* argv[2u + sizeof...(TArgs)]
+                = {const_cast<void*>(static_cast<void const*>(&threadElemExtent)),
+                   const_cast<void*>(static_cast<void const*>(&kernelFnObj)),
+                   const_cast<void*>(static_cast<void const*>(&args))...};
+
+            check(b200_launch(
+                getDev(queue).getNativeHandle(),
+                reinterpret_cast<void const*>(kernel),
+                grid,
+                block,
+                dynSmemBytes,
+                queue.getNativeHandle(),
+                argv));
+#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
+            // debug builds surface asynchronous launch failures at the launch site, like the reference
+            check(b200_stream_sync(queue.getNativeHandle()));
+#    endif
+        }
+    } // namespace b200
 #endif
 
     namespace detail
@@ -264,13 +334,16 @@ namespace alpaka
                     if(b200::nativeKernelsEnabled())
                     {
                         bool const handled = std::apply(
-                            [&](auto const&... args)
+                            [&](auto const&... args) -> bool
                             {
-                                return NativeKernel<TKernelFnObj, TAcc>::launch(
-                                    queue,
-                                    static_cast<WorkDivMembers<TDim, TIdx> const&>(task),
-                                    task.m_kernelFnObj,
-                                    args...);
+                                auto const& workDiv = static_cast<WorkDivMembers<TDim, TIdx> const&>(task);
+                                // only offered if the specialisation's signature accepts these argument types
+                                if constexpr(requires {
+                                                 NativeKernel<TKernelFnObj, TAcc>::launch(queue, workDiv, task.m_kernelFnObj, args...);
+                                             })
+                                    return NativeKernel<TKernelFnObj, TAcc>::launch(queue, workDiv, task.m_kernelFnObj, args...);
+                                else
+                                    return false;
                             },
                             task.m_args);
                         if(handled)
@@ -282,56 +355,16 @@ namespace alpaka
                 }
 
                 // 2. generic trampoline
-                auto const gridBlockExtent = getWorkDiv<Grid, Blocks>(task);
-                auto const blockThreadExtent = getWorkDiv<Block, Threads>(task);
-                auto threadElemExtent = getWorkDiv<Thread, Elems>(task);
-
-                uint32_t grid[3] = {1u, 1u, 1u};
-                uint32_t block[3] = {1u, 1u, 1u};
-                for(std::size_t d = 0; d < TDim::value; ++d)
-                {
-                    // alpaka's fastest (last) dimension is CUDA x
-                    grid[d] = static_cast<uint32_t>(gridBlockExtent[TDim::value - 1u - d]);
-                    block[d] = static_cast<uint32_t>(blockThreadExtent[TDim::value - 1u - d]);
-                }
-
-#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
-                if(!isValidWorkDiv<TAcc>(task, getDev(queue)))
-                    throw std::runtime_error(
-                        "The given work division is not valid or not supported by the device of type "
-                        + getAccName<TAcc>() + "!");
-#    endif
-                std::size_t const dynSmemBytes = std::apply(
+                std::apply(
                     [&](auto const&... args)
                     {
-                        return getBlockSharedMemDynSizeBytes<TAcc>(task.m_kernelFnObj, blockThreadExtent, threadElemExtent, args...);
+                        b200::launchGeneric<TAcc>(
+                            queue,
+                            static_cast<WorkDivMembers<TDim, TIdx> const&>(task),
+                            task.m_kernelFnObj,
+                            args...);
                     },
                     task.m_args);
-
-                auto const kernel = b200k::run<TKernelFnObj, TAcc, TDim, TIdx, std::decay_t<TArgs>...>;
-
-                // cudaLaunchKernel wants one pointer per kernel parameter, in order
-                constexpr std::size_t nArgs = sizeof...(TArgs);
-                void* argv[2u + nArgs];
-                argv[0] = const_cast<void*>(static_cast<void const*>(&threadElemExtent));
-                argv[1] = const_cast<void*>(static_cast<void const*>(&task.m_kernelFnObj));
-                std::size_t i = 2u;
-                std::apply(
-                    [&](auto const&... args) { ((argv[i++] = const_cast<void*>(static_cast<void const*>(&args))), ...); },
-                    task.m_args);
-
-                b200::check(b200_launch(
-                    getDev(queue).getNativeHandle(),
-                    reinterpret_cast<void const*>(kernel),
-                    grid,
-                    block,
-                    dynSmemBytes,
-                    queue.getNativeHandle(),
-                    argv));
-#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
-                // debug builds surface asynchronous launch failures at the launch site, like the reference
-                b200::check(b200_stream_sync(queue.getNativeHandle()));
-#    endif
                 queue.afterEnqueue();
             }
         };

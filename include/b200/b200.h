@@ -290,6 +290,11 @@ extern "C"
      * (used to split interior / edge strips for halo overlap). */
     int b200_heat2d_step_window_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1);
 
+    /* The ring alone, as its own small launch: BoundaryKernel (BoundaryKernel.hpp:24-86) for callers that keep the
+     * reference's two-launch step (the alpaka API layer running the unmodified driver). Writes the analytic value to
+     * the ring of buffer `dst_index` on the sides flagged in the plan's `edges`. */
+    int b200_heat2d_boundary_f64(b200_heat2d_plan_t plan, b200_stream_t s, int dst_index, double time_factor);
+
     /* ---------------------------------------------------------------------------------------------
      * Tuning / introspection (bench + profiling only)
      * ------------------------------------------------------------------------------------------- */
