@@ -7,7 +7,7 @@ from ._lib import B200Error
 
 _lib.load()  # fail loudly if the CUDA library has not been built
 
-from . import babelstream, heat2d, reduce, runtime, workdiv  # noqa: E402
+from . import babelstream, decomp, heat2d, multi, reduce, runtime, workdiv  # noqa: E402
 from .runtime import (  # noqa: E402
     Buf,
     Dev,
@@ -29,6 +29,6 @@ from .runtime import (  # noqa: E402
 
 __all__ = [
     "B200Error", "Buf", "Dev", "Event", "HostBuf", "Platform", "Queue", "alloc_async_buf", "alloc_buf",
-    "alloc_mapped_buf", "babelstream", "create_view", "enqueue", "get_dev_by_idx", "get_dev_count", "heat2d", "memcpy", "memset",
+    "alloc_mapped_buf", "babelstream", "create_view", "decomp", "multi", "enqueue", "get_dev_by_idx", "get_dev_count", "heat2d", "memcpy", "memset",
     "reduce", "runtime", "wait", "workdiv",
 ]

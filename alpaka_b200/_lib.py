@@ -68,6 +68,16 @@ class AccDevProps(C.Structure):
     ]
 
 
+class Heat2dHalo(C.Structure):
+    """b200_heat2d_halo: peer pointers and flag words of the fused halo exchange (side order top, bottom, left, right)."""
+
+    _fields_ = [
+        ("peer_u", (C.c_void_p * 2) * 4),
+        ("peer_flag", C.c_void_p * 4),
+        ("my_flags", C.c_void_p),
+    ]
+
+
 _vp, _u64, _u32, _i, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
 _f64, _f32 = C.c_double, C.c_float
 _P = C.POINTER
@@ -149,6 +159,10 @@ SIGNATURES: dict[str, list] = {
     "b200_heat2d_plan_destroy": [_vp],
     "b200_heat2d_step_f64": [_vp, _vp, _i, _f64, _f64, _f64],
     "b200_heat2d_step_window_f64": [_vp, _vp, _i, _f64, _f64, _f64, _u32, _u32, _u32, _u32],
+    "b200_heat2d_boundary_f64": [_vp, _vp, _i, _f64],
+    "b200_heat2d_plan_set_halo": [_vp, _P(Heat2dHalo)],
+    "b200_heat2d_step_halo_f64": [_vp, _vp, _i, _f64, _f64, _f64, _u32],
+    "b200_heat2d_halo_status": [_vp, _P(_u32)],
     "b200_tune_set": [C.c_char_p, C.c_int64],
     "b200_tune_get": [C.c_char_p, _P(C.c_int64)],
     "b200_launch_count": [],

@@ -47,19 +47,40 @@ namespace
         return (TX / 2) * (TY / rpt);
     }
 
+    constexpr int kMaxWindows = 5;
+
+    // One rectangular window of OUTPUT cells [j0,j1) x [i0,i1) in padded coordinates, cut into TY x TX tiles whose grid
+    // starts at (j0, iw0). A launch processes up to kMaxWindows windows, tiles numbered window by window.
+    struct HeatWindow
+    {
+        uint32_t j0, j1, i0, i1;
+        uint32_t iw0; // i0 rounded down to even: tile grid origin
+        uint32_t tilesX;
+        uint32_t tileBegin; // index of this window's first tile
+        uint32_t strip; // 1: edge strip of a decomposed tile (its border cells are also stored into the neighbours' ghosts)
+    };
+
     struct HeatArgs
     {
         double* dst;
         size_t pitchElems;
         uint32_t ny, nx;
-        uint32_t j0, j1, i0, i1; // output window, padded coordinates
-        uint32_t iw0; // i0 rounded down to even: tile grid origin
-        uint32_t tilesX, tilesY;
+        HeatWindow win[kMaxWindows];
+        int nWin;
+        uint32_t totalTiles;
         double k, rX, rY, tf;
         double const* sx;
         double const* sy;
         int edges;
         int stages;
+        // ---- fused halo exchange (2-D decomposition); all null / 0 for a stand-alone field
+        double* peerDst[4]; // [top, bottom, left, right]: the neighbour's DESTINATION buffer of this step, or null
+        uint32_t* peerFlag[4]; // slot in the neighbour's flag array that this rank sets to `step`
+        uint32_t* myFlags; // [4] slots set by the neighbours: "my step-s border cells are in your ghosts"
+        uint32_t* stripCounter; // strip tiles finished in this launch (reset by the last one)
+        uint32_t* status; // != 0: a flag wait timed out
+        uint32_t stripTiles;
+        uint32_t step; // 1-based time level this launch produces
     };
 
     __device__ __forceinline__ uint32_t smemAddr(void const* p)
@@ -162,16 +183,22 @@ namespace
         __shared__ uint64_t full[kMaxStages];
         __shared__ uint64_t empty[kMaxStages];
 
-        uint32_t const totalTiles = A.tilesX * A.tilesY;
+        uint32_t const totalTiles = A.totalTiles;
         int const tid = threadIdx.x;
         int const stages = A.stages;
 
-        auto tileOrigin = [&](uint32_t t, uint32_t& y0, uint32_t& x0)
+        // tile index -> window and tile origin
+        auto tileOrigin = [&](uint32_t t, uint32_t& y0, uint32_t& x0) -> int
         {
-            uint32_t const ty = t / A.tilesX;
-            uint32_t const tx = t - ty * A.tilesX;
-            y0 = A.j0 + ty * TY;
-            x0 = A.iw0 + tx * TX;
+            int w = A.nWin - 1;
+            while(w > 0 && t < A.win[w].tileBegin)
+                --w;
+            uint32_t const local = t - A.win[w].tileBegin;
+            uint32_t const ty = local / A.win[w].tilesX;
+            uint32_t const tx = local - ty * A.win[w].tilesX;
+            y0 = A.win[w].j0 + ty * TY;
+            x0 = A.win[w].iw0 + tx * TX;
+            return w;
         };
 
         if(tid == 0)
@@ -182,6 +209,33 @@ namespace
                 mbarInit(&empty[s], kConsumerWarps);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if(A.myFlags != nullptr)
+            {
+                // The ghost cells this launch reads hold the neighbours' border cells of time level step-1 once their
+                // flags say so. Bounded spin (about 2 s): a peer that died must not hang this GPU.
+                for(int side = 0; side < 4; ++side)
+                {
+                    if(A.peerDst[side] == nullptr)
+                        continue;
+                    uint32_t seen = 0;
+                    uint32_t spins = 0;
+                    for(;;)
+                    {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
+                        if(seen + 1u >= A.step + 0u) // seen >= step - 1 without underflow at step 0
+                            break;
+                        if(++spins > 2000000u)
+                        {
+                            atomicExch(A.status, 1u + uint32_t(side));
+                            break;
+                        }
+                        __nanosleep(1000);
+                    }
+                }
+                // the ghosts were written through the generic proxy (peer stores); the TMA unit reads them through the
+                // async proxy
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
         }
         __syncthreads();
 
@@ -196,7 +250,7 @@ namespace
                 {
                     mbarWait(&empty[s], parity);
                     uint32_t y0, x0;
-                    tileOrigin(t, y0, x0);
+                    (void) tileOrigin(t, y0, x0);
                     mbarExpectTx(&full[s], BOX_BYTES);
                     tmaLoad2d(smem + size_t(s) * STAGE_BYTES, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 1, &full[s]);
                     if(++s == stages)
@@ -217,7 +271,7 @@ namespace
         for(uint32_t t = blockIdx.x; t < totalTiles; t += gridDim.x)
         {
             uint32_t y0, x0;
-            tileOrigin(t, y0, x0);
+            HeatWindow const& W = A.win[tileOrigin(t, y0, x0)];
             mbarWait(&full[s], parity);
 
             double const* box = reinterpret_cast<double const*>(smem + size_t(s) * STAGE_BYTES);
@@ -228,8 +282,8 @@ namespace
             double2 cl = lds128(p + BOX_X), cc = lds128(p + BOX_X + 2), cr = lds128(p + BOX_X + 4);
 
             uint32_t const gi = x0 + 2 * cp; // global (padded) column of the pair's first cell
-            bool const fast = y0 >= 1 && y0 + TY <= A.ny + 1 && y0 >= A.j0 && y0 + TY <= A.j1 && x0 >= 1
-                              && x0 + TX <= A.nx + 1 && x0 >= A.i0 && x0 + TX <= A.i1;
+            bool const fast = !W.strip && y0 >= 1 && y0 + TY <= A.ny + 1 && y0 >= W.j0 && y0 + TY <= W.j1 && x0 >= 1
+                              && x0 + TX <= A.nx + 1 && x0 >= W.i0 && x0 + TX <= W.i1;
             double* out = A.dst + size_t(y0 + r0) * A.pitchElems + gi;
 #pragma unroll
             for(int r = 0; r < RPT; ++r)
@@ -246,14 +300,21 @@ namespace
                 {
                     uint32_t const gj = y0 + r0 + r;
                     bool w0 = false, w1 = false;
+                    bool core0 = false, core1 = false;
                     double o0 = v0, o1 = v1;
-                    if(gj >= A.j0 && gj < A.j1 && gj <= A.ny + 1)
+                    if(gj >= W.j0 && gj < W.j1 && gj <= A.ny + 1)
                     {
                         bool const jCore = gj >= 1 && gj <= A.ny;
-                        if(gi >= A.i0 && gi < A.i1 && gi <= A.nx + 1)
-                            w0 = (jCore && gi >= 1 && gi <= A.nx) ? true : ringValue(A, gj, gi, o0);
-                        if(gi + 1 >= A.i0 && gi + 1 < A.i1 && gi + 1 <= A.nx + 1)
-                            w1 = (jCore && gi + 1 >= 1 && gi + 1 <= A.nx) ? true : ringValue(A, gj, gi + 1, o1);
+                        if(gi >= W.i0 && gi < W.i1 && gi <= A.nx + 1)
+                        {
+                            core0 = jCore && gi >= 1 && gi <= A.nx;
+                            w0 = core0 ? true : ringValue(A, gj, gi, o0);
+                        }
+                        if(gi + 1 >= W.i0 && gi + 1 < W.i1 && gi + 1 <= A.nx + 1)
+                        {
+                            core1 = jCore && gi + 1 >= 1 && gi + 1 <= A.nx;
+                            w1 = core1 ? true : ringValue(A, gj, gi + 1, o1);
+                        }
                     }
                     if(w0 && w1)
                         stg2<HINT>(out, o0, o1);
@@ -261,6 +322,39 @@ namespace
                         out[0] = o0;
                     else if(w1)
                         out[1] = o1;
+                    if(W.strip)
+                    {
+                        // fused halo exchange: the border cells of this tile are the neighbours' ghost cells. Peer stores
+                        // (NVLink) straight from the registers that hold the fresh values; tiles have equal extents, so
+                        // the neighbour's padded coordinates mirror ours.
+                        if(core0 || core1)
+                        {
+                            if(gj == 1u && A.peerDst[0] != nullptr)
+                            {
+                                double* row = A.peerDst[0] + size_t(A.ny + 1u) * A.pitchElems + gi;
+                                if(core0)
+                                    row[0] = v0;
+                                if(core1)
+                                    row[1] = v1;
+                            }
+                            if(gj == A.ny && A.peerDst[1] != nullptr)
+                            {
+                                double* row = A.peerDst[1] + gi;
+                                if(core0)
+                                    row[0] = v0;
+                                if(core1)
+                                    row[1] = v1;
+                            }
+                        }
+                        if(core1 && gi + 1u == 1u && A.peerDst[2] != nullptr)
+                            A.peerDst[2][size_t(gj) * A.pitchElems + A.nx + 1u] = v1;
+                        if(core0 && gi == 1u && A.peerDst[2] != nullptr)
+                            A.peerDst[2][size_t(gj) * A.pitchElems + A.nx + 1u] = v0;
+                        if(core0 && gi == A.nx && A.peerDst[3] != nullptr)
+                            A.peerDst[3][size_t(gj) * A.pitchElems] = v0;
+                        if(core1 && gi + 1u == A.nx && A.peerDst[3] != nullptr)
+                            A.peerDst[3][size_t(gj) * A.pitchElems] = v1;
+                    }
                 }
                 up = cc;
                 cl = nl;
@@ -278,9 +372,28 @@ namespace
                 s = 0;
                 parity ^= 1u;
             }
+
+            if(W.strip && A.stripCounter != nullptr)
+            {
+                // all consumer warps have issued this strip tile's (peer) stores; count the tile, and let whoever
+                // finishes the LAST strip tile of the launch publish the time level to the neighbours
+                asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+                if(tid == 0)
+                {
+                    __threadfence_system();
+                    uint32_t const done = atomicAdd(A.stripCounter, 1u);
+                    if(done == A.stripTiles - 1u)
+                    {
+                        __threadfence_system();
+                        *A.stripCounter = 0u; // ready for the next launch
+                        for(int side = 0; side < 4; ++side)
+                            if(A.peerFlag[side] != nullptr)
+                                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
+                    }
+                }
+            }
         }
     }
-
 
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
     // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
@@ -365,6 +478,10 @@ struct b200_heat2d_plan_st
     double* sx;
     double* sy;
     CUtensorMap map[2];
+    // fused halo exchange (b200_heat2d_plan_set_halo)
+    bool hasHalo = false;
+    b200_heat2d_halo halo{};
+    uint32_t* haloScratch = nullptr; // [0] strip-tile counter, [1] status
 };
 
 extern "C"
@@ -465,9 +582,94 @@ extern "C"
         B200_CUDA(cudaSetDevice(plan->dev));
         B200_CUDA(cudaFree(plan->sx));
         B200_CUDA(cudaFree(plan->sy));
+        if(plan->haloScratch != nullptr)
+            B200_CUDA(cudaFree(plan->haloScratch));
         delete plan;
         return 0;
     }
+
+    namespace
+    {
+        // appends window [j0,j1) x [i0,i1) to the launch description (skipped when empty)
+        void addWindow(HeatArgs& A, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1, uint32_t strip)
+        {
+            if(j0 >= j1 || i0 >= i1)
+                return;
+            HeatWindow& W = A.win[A.nWin++];
+            W.j0 = j0;
+            W.j1 = j1;
+            W.i0 = i0;
+            W.i1 = i1;
+            W.iw0 = i0 & ~1u;
+            W.tilesX = (i1 - W.iw0 + TX - 1) / TX;
+            W.tileBegin = A.totalTiles;
+            W.strip = strip;
+            uint32_t const tilesY = (j1 - j0 + TY - 1) / TY;
+            A.totalTiles += W.tilesX * tilesY;
+            if(strip)
+                A.stripTiles += W.tilesX * tilesY;
+        }
+
+        HeatArgs baseArgs(b200_heat2d_plan_t plan, int src_index, double rx, double ry, double time_factor)
+        {
+            HeatArgs A{};
+            A.dst = plan->u[1 - src_index];
+            A.pitchElems = plan->pitchBytes / 8;
+            A.ny = plan->ny;
+            A.nx = plan->nx;
+            // StencilKernel.hpp:84: (1.0 - 2.0 * rX - 2.0 * rY), evaluated left to right in IEEE double on the host
+            // (this TU is built with -ffp-contract=off for host code)
+            A.rX = rx;
+            A.rY = ry;
+            A.k = 1.0 - 2.0 * rx - 2.0 * ry;
+            A.tf = time_factor;
+            A.sx = plan->sx;
+            A.sy = plan->sy;
+            A.edges = plan->edges;
+            int stages = int(b200::tune("heat.stages", 2));
+            A.stages = stages < 1 ? 1 : (stages > kMaxStages ? kMaxStages : stages);
+            return A;
+        }
+
+        int launchHeat(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, HeatArgs const& A)
+        {
+            if(A.totalTiles == 0)
+                return 0;
+            int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 1));
+            int const hint = int(b200::tune("heat.hint", 1));
+            uint64_t grid = uint64_t(b200::smCount(plan->dev)) * (ctasPerSm > 0 ? ctasPerSm : 1);
+            // heat.grid_cap: upper bound on CTAs per launch. Needed when several decomposed tiles share ONE device
+            // (tests): their kernels wait for each other's flags, so all of them must be resident at the same time.
+            int64_t const cap = b200::tune("heat.grid_cap", 0);
+            if(cap > 0 && grid > uint64_t(cap))
+                grid = uint64_t(cap);
+            if(grid > A.totalTiles)
+                grid = A.totalTiles;
+            auto const s = reinterpret_cast<cudaStream_t>(stream);
+            size_t const smemBytes = size_t(A.stages) * STAGE_BYTES;
+            int const rpt = int(b200::tune("heat.rpt", 4));
+            auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map[src_index], A); };
+            switch(rpt * 2 + (hint ? 1 : 0))
+            {
+            case 17:
+                launch(heatStepKernel<1, 8>, consumerThreads(8) + 32);
+                break;
+            case 16:
+                launch(heatStepKernel<0, 8>, consumerThreads(8) + 32);
+                break;
+            case 9:
+                launch(heatStepKernel<1, 4>, consumerThreads(4) + 32);
+                break;
+            case 8:
+                launch(heatStepKernel<0, 4>, consumerThreads(4) + 32);
+                break;
+            default:
+                return b200::fail(B200_EINVAL, "heat.rpt must be 4 or 8", __FILE__, __LINE__);
+            }
+            B200_LAUNCH_CHECK();
+            return 0;
+        }
+    } // namespace
 
     int b200_heat2d_step_window_f64(
         b200_heat2d_plan_t plan,
@@ -483,65 +685,10 @@ extern "C"
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1), B200_EINVAL);
         B200_REQUIRE(j1 <= plan->ny + 2 && i1 <= plan->nx + 2, B200_EINVAL);
-        if(j0 >= j1 || i0 >= i1)
-            return 0;
-        HeatArgs A{};
-        A.dst = plan->u[1 - src_index];
-        A.pitchElems = plan->pitchBytes / 8;
-        A.ny = plan->ny;
-        A.nx = plan->nx;
-        A.j0 = j0;
-        A.j1 = j1;
-        A.i0 = i0;
-        A.i1 = i1;
-        A.iw0 = i0 & ~1u;
-        A.tilesX = (i1 - A.iw0 + TX - 1) / TX;
-        A.tilesY = (j1 - j0 + TY - 1) / TY;
-        // StencilKernel.hpp:84: (1.0 - 2.0 * rX - 2.0 * rY), evaluated left to right in IEEE double on the host
-        // (this TU is built with -ffp-contract=off for host code)
-        A.rX = rx;
-        A.rY = ry;
-        A.k = 1.0 - 2.0 * rx - 2.0 * ry;
-        A.tf = time_factor;
-        A.sx = plan->sx;
-        A.sy = plan->sy;
-        A.edges = plan->edges;
-        int stages = int(b200::tune("heat.stages", 2));
-        if(stages < 1)
-            stages = 1;
-        if(stages > kMaxStages)
-            stages = kMaxStages;
-        A.stages = stages;
-        int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 1));
-        int const hint = int(b200::tune("heat.hint", 1));
-        uint64_t const total = uint64_t(A.tilesX) * A.tilesY;
-        B200_REQUIRE(total < 0xffffffffull, B200_ERANGE);
-        uint64_t grid = uint64_t(b200::smCount(plan->dev)) * (ctasPerSm > 0 ? ctasPerSm : 1);
-        if(grid > total)
-            grid = total;
-        auto const s = reinterpret_cast<cudaStream_t>(stream);
-        size_t const smemBytes = size_t(stages) * STAGE_BYTES;
-        int const rpt = int(b200::tune("heat.rpt", 4));
-        auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map[src_index], A); };
-        switch(rpt * 2 + (hint ? 1 : 0))
-        {
-        case 17:
-            launch(heatStepKernel<1, 8>, consumerThreads(8) + 32);
-            break;
-        case 16:
-            launch(heatStepKernel<0, 8>, consumerThreads(8) + 32);
-            break;
-        case 9:
-            launch(heatStepKernel<1, 4>, consumerThreads(4) + 32);
-            break;
-        case 8:
-            launch(heatStepKernel<0, 4>, consumerThreads(4) + 32);
-            break;
-        default:
-            return b200::fail(B200_EINVAL, "heat.rpt must be 4 or 8", __FILE__, __LINE__);
-        }
-        B200_LAUNCH_CHECK();
-        return 0;
+        B200_CUDA(cudaSetDevice(plan->dev));
+        HeatArgs A = baseArgs(plan, src_index, rx, ry, time_factor);
+        addWindow(A, j0, j1, i0, i1, 0);
+        return launchHeat(plan, stream, src_index, A);
     }
 
     int b200_heat2d_boundary_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int dst_index, double time_factor)
@@ -567,5 +714,72 @@ extern "C"
     {
         B200_REQUIRE(plan, B200_EINVAL);
         return b200_heat2d_step_window_f64(plan, s, src_index, rx, ry, time_factor, 0, plan->ny + 2, 0, plan->nx + 2);
+    }
+
+    int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo)
+    {
+        B200_REQUIRE(plan && halo && halo->my_flags, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(plan->dev));
+        for(int side = 0; side < 4; ++side)
+        {
+            bool const hasNeighbour = halo->peer_u[side][0] != nullptr;
+            B200_REQUIRE(hasNeighbour == (halo->peer_u[side][1] != nullptr), B200_EINVAL);
+            B200_REQUIRE(hasNeighbour == (halo->peer_flag[side] != nullptr), B200_EINVAL);
+            // a side is either a physical boundary (plan `edges`) or has a neighbour, never both
+            int const bit = side == 0 ? B200_EDGE_TOP : side == 1 ? B200_EDGE_BOTTOM : side == 2 ? B200_EDGE_LEFT : B200_EDGE_RIGHT;
+            B200_REQUIRE(hasNeighbour != ((plan->edges & bit) != 0), B200_EINVAL);
+        }
+        if(plan->haloScratch == nullptr)
+        {
+            B200_CUDA(cudaMalloc(reinterpret_cast<void**>(&plan->haloScratch), 64));
+            B200_CUDA(cudaMemset(plan->haloScratch, 0, 64));
+        }
+        plan->halo = *halo;
+        plan->hasHalo = true;
+        return 0;
+    }
+
+    int b200_heat2d_step_halo_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, double rx, double ry, double time_factor, uint32_t step)
+    {
+        B200_REQUIRE(plan && plan->hasHalo && (src_index == 0 || src_index == 1) && step >= 1, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(plan->dev));
+        HeatArgs A = baseArgs(plan, src_index, rx, ry, time_factor);
+        uint32_t const H = plan->ny + 2, Wd = plan->nx + 2;
+        // Edge strips first (their border cells travel to the neighbours while the interior is computed), each one
+        // tile thick so that no tile is fetched for a sliver; then the interior. Small tiles: everything is "strip".
+        if(H > 2 * TY && Wd > 2 * TX)
+        {
+            addWindow(A, 0, TY, 0, Wd, 1); // top
+            addWindow(A, H - TY, H, 0, Wd, 1); // bottom
+            addWindow(A, TY, H - TY, 0, TX, 1); // left
+            addWindow(A, TY, H - TY, Wd - TX, Wd, 1); // right
+            addWindow(A, TY, H - TY, TX, Wd - TX, 0); // interior
+        }
+        else
+        {
+            addWindow(A, 0, H, 0, Wd, 1);
+        }
+        int const dstIndex = 1 - src_index;
+        for(int side = 0; side < 4; ++side)
+        {
+            A.peerDst[side] = plan->halo.peer_u[side][dstIndex];
+            A.peerFlag[side] = plan->halo.peer_flag[side];
+        }
+        A.myFlags = plan->halo.my_flags;
+        A.stripCounter = plan->haloScratch;
+        A.status = plan->haloScratch + 1;
+        A.step = step;
+        return launchHeat(plan, stream, src_index, A);
+    }
+
+    int b200_heat2d_halo_status(b200_heat2d_plan_t plan, uint32_t* status)
+    {
+        B200_REQUIRE(plan && status, B200_EINVAL);
+        *status = 0;
+        if(plan->haloScratch == nullptr)
+            return 0;
+        B200_CUDA(cudaSetDevice(plan->dev));
+        B200_CUDA(cudaMemcpy(status, plan->haloScratch + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        return 0;
     }
 }

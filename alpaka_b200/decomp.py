@@ -1,0 +1,120 @@
+"""Host-side partitioning logic of the multi-GPU layer -- pure Python, no device needed, so the
+world_size > 1 logic is testable on CPU with the gloo backend (tests/test_multi_rank_cpu.py).
+
+  * streams / Dot / reduce: contiguous slabs, rank r owns [lo, hi) of every array; no exchange except one scalar.
+  * heatEquation2D: Py x Px process grid over the NY x NX core cells; every rank owns an equal (ny+2) x (nx+2) tile
+    whose outer ring is either the physical boundary (BoundaryKernel semantics) or ghost cells owned by a neighbour.
+The reference has nothing of this (every driver uses device 0); parity is defined as "decomposed result == undecomposed
+oracle result", bit for bit."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+EDGE_TOP, EDGE_BOTTOM, EDGE_LEFT, EDGE_RIGHT = 1, 2, 4, 8
+SIDES = ("top", "bottom", "left", "right")
+OPPOSITE = {"top": "bottom", "bottom": "top", "left": "right", "right": "left"}
+
+
+def slab_bounds(n: int, world: int, rank: int, align: int = 1) -> tuple[int, int]:
+    """[lo, hi) of rank's contiguous slab of n elements; slab starts are multiples of `align` elements (16-byte
+    boundaries for the vector loads), the last rank takes the remainder; lower ranks never get fewer elements."""
+    if world < 1 or not (0 <= rank < world) or n < 0 or align < 1:
+        raise ValueError("slab_bounds: bad arguments")
+    per = -(-n // world)  # ceil
+    per = -(-per // align) * align
+    lo = min(rank * per, n)
+    hi = min(lo + per, n)
+    return lo, hi
+
+
+def process_grid(world: int) -> tuple[int, int]:
+    """(Py, Px) with Py * Px == world, as square as possible, Py >= Px: rows are split first because a row halo is
+    contiguous in memory and a column halo is strided. 1 -> 1x1, 2 -> 2x1, 4 -> 2x2, 8 -> 4x2."""
+    if world < 1:
+        raise ValueError("process_grid: world must be >= 1")
+    px = int(world**0.5)
+    while world % px != 0:
+        px -= 1
+    return world // px, px
+
+
+@dataclass(frozen=True)
+class Tile:
+    """One rank's share of the heat field. Local padded coordinates [0, ny+2) x [0, nx+2); local [j][i] is global
+    padded [j + j_offset][i + i_offset]."""
+
+    rank: int
+    py: int
+    px: int
+    cy: int
+    cx: int
+    ny: int
+    nx: int
+    j_offset: int
+    i_offset: int
+    edges: int
+    neighbours: dict = field(default_factory=dict)  # side -> rank or None
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self.ny + 2, self.nx + 2
+
+
+def tile_for(rank: int, world: int, NY: int, NX: int, grid: Optional[tuple[int, int]] = None) -> Tile:
+    py, px = grid if grid is not None else process_grid(world)
+    if py * px != world:
+        raise ValueError("tile_for: process grid does not match the world size")
+    if NY % py != 0 or NX % px != 0:
+        raise ValueError(f"tile_for: {NY} x {NX} core cells do not divide over a {py} x {px} process grid")
+    cy, cx = divmod(rank, px)
+    ny, nx = NY // py, NX // px
+    edges = 0
+    nb: dict = {}
+    nb["top"] = None if cy == 0 else (cy - 1) * px + cx
+    nb["bottom"] = None if cy == py - 1 else (cy + 1) * px + cx
+    nb["left"] = None if cx == 0 else cy * px + (cx - 1)
+    nb["right"] = None if cx == px - 1 else cy * px + (cx + 1)
+    for side, bit in zip(SIDES, (EDGE_TOP, EDGE_BOTTOM, EDGE_LEFT, EDGE_RIGHT)):
+        if nb[side] is None:
+            edges |= bit
+    return Tile(rank, py, px, cy, cx, ny, nx, cy * ny, cx * nx, edges, nb)
+
+
+def tile_view(global_field, tile: Tile):
+    """The tile's (ny+2) x (nx+2) window of a global (NY+2) x (NX+2) padded field (ghosts included)."""
+    return global_field[tile.j_offset : tile.j_offset + tile.ny + 2, tile.i_offset : tile.i_offset + tile.nx + 2]
+
+
+def stitch(global_out, tile: Tile, local_field) -> None:
+    """Writes the cells the tile OWNS into the global field: its core cells plus the physical ring on its boundary
+    sides (ghost cells belong to the neighbours and are skipped)."""
+    j0 = 0 if tile.edges & EDGE_TOP else 1
+    j1 = tile.ny + 2 if tile.edges & EDGE_BOTTOM else tile.ny + 1
+    i0 = 0 if tile.edges & EDGE_LEFT else 1
+    i1 = tile.nx + 2 if tile.edges & EDGE_RIGHT else tile.nx + 1
+    global_out[tile.j_offset + j0 : tile.j_offset + j1, tile.i_offset + i0 : tile.i_offset + i1] = local_field[j0:j1, i0:i1]
+
+
+def halo_slices(tile: Tile, side: str):
+    """(send, recv) index expressions in local padded coordinates for the exchange with the neighbour on `side`:
+    `send` = my border core cells, `recv` = my ghost cells on that side."""
+    ny, nx = tile.ny, tile.nx
+    if side == "top":
+        return (slice(1, 2), slice(1, nx + 1)), (slice(0, 1), slice(1, nx + 1))
+    if side == "bottom":
+        return (slice(ny, ny + 1), slice(1, nx + 1)), (slice(ny + 1, ny + 2), slice(1, nx + 1))
+    if side == "left":
+        return (slice(1, ny + 1), slice(1, 2)), (slice(1, ny + 1), slice(0, 1))
+    if side == "right":
+        return (slice(1, ny + 1), slice(nx, nx + 1)), (slice(1, ny + 1), slice(nx + 1, nx + 2))
+    raise ValueError(side)
+
+
+def combine_in_rank_order(parts):
+    """The Dot / float-reduce exchange step: one scalar per rank, summed left to right in rank order so the result
+    does not depend on the collective's internal order."""
+    total = parts[0]
+    for p in parts[1:]:
+        total = total + p
+    return total

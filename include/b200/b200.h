@@ -290,6 +290,31 @@ extern "C"
      * (used to split interior / edge strips for halo overlap). */
     int b200_heat2d_step_window_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1);
 
+    /* ---- 2-D decomposition with the halo exchange FUSED into the step kernel (new; the reference is single-device,
+     * SURVEY.md section 8e). Every rank owns a tile of identical extents (ny+2) x (nx+2) and pitch; a side is either a
+     * physical boundary (plan `edges`) or has a neighbour. One launch per step: the edge strips are computed first and
+     * their border cells are ALSO stored straight into the neighbour's ghost cells through peer pointers (NVLink P2P
+     * stores from the registers holding the fresh values), then the interior; the CTA that finishes the last strip
+     * tile publishes the time level in the neighbours' flag words (st.release.sys), and a launch starts by waiting
+     * (ld.acquire.sys, bounded) until its own flag words say the ghosts of the previous time level have arrived. No
+     * host synchronisation, no staging copies, no NCCL. Pointers may be CUDA-IPC mappings (one process per GPU) or plain
+     * peer-enabled device pointers (one process, several GPUs).
+     *   peer_u[side][b]  neighbour's ping-pong buffer b (same order as this plan's u0/u1), side = 0 top (j=0), 1 bottom,
+     *                    2 left (i=0), 3 right; NULL on a physical boundary
+     *   peer_flag[side]  the word in the NEIGHBOUR's flag array that this rank sets (its slot for the opposite side)
+     *   my_flags         this rank's 4 words, zero-initialised, written by the neighbours (slot order as `side`)
+     * `step` is the 1-based time level the launch produces; ghosts of the initial field count as level 0. */
+    typedef struct b200_heat2d_halo
+    {
+        double* peer_u[4][2];
+        uint32_t* peer_flag[4];
+        uint32_t* my_flags;
+    } b200_heat2d_halo;
+    int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo);
+    int b200_heat2d_step_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t step);
+    /* 0, or 1 + side of the first flag wait that timed out (a neighbour stopped making progress). Synchronous. */
+    int b200_heat2d_halo_status(b200_heat2d_plan_t plan, uint32_t* status);
+
     /* The ring alone, as its own small launch: BoundaryKernel (BoundaryKernel.hpp:24-86) for callers that keep the
      * reference's two-launch step (the alpaka API layer running the unmodified driver). Writes the analytic value to
      * the ring of buffer `dst_index` on the sides flagged in the plan's `edges`. */
