@@ -209,9 +209,10 @@ namespace
                 mbarInit(&empty[s], kConsumerWarps);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            if(A.myFlags != nullptr)
+            if(A.myFlags != nullptr && blockIdx.x < A.stripTiles)
             {
-                // The ghost cells this launch reads hold the neighbours' border cells of time level step-1 once their
+                // Only strip tiles read ghost cells, and they come first in the tile order: CTAs without a strip
+                // tile skip the wait. The ghost cells this launch reads hold the neighbours' border cells of time level step-1 once their
                 // flags say so. Bounded spin (about 2 s): a peer that died must not hang this GPU.
                 for(int side = 0; side < 4; ++side)
                 {
@@ -282,8 +283,9 @@ namespace
             double2 cl = lds128(p + BOX_X), cc = lds128(p + BOX_X + 2), cr = lds128(p + BOX_X + 4);
 
             uint32_t const gi = x0 + 2 * cp; // global (padded) column of the pair's first cell
-            bool const fast = !W.strip && y0 >= 1 && y0 + TY <= A.ny + 1 && y0 >= W.j0 && y0 + TY <= W.j1 && x0 >= 1
-                              && x0 + TX <= A.nx + 1 && x0 >= W.i0 && x0 + TX <= W.i1;
+            // all TX columns of the tile are core cells inside the window: rows that are core rows inside the window
+            // take the vector store without per-cell tests
+            bool const colsInside = x0 >= 1 && x0 >= W.i0 && x0 + TX <= A.nx + 1 && x0 + TX <= W.i1;
             double* out = A.dst + size_t(y0 + r0) * A.pitchElems + gi;
 #pragma unroll
             for(int r = 0; r < RPT; ++r)
@@ -292,13 +294,22 @@ namespace
                 double2 const nl = lds128(q), nc = lds128(q + 2), nr = lds128(q + 4);
                 double const v0 = ftcs(cc.x, cl.y, cc.y, up.x, nc.x, A.k, A.rX, A.rY);
                 double const v1 = ftcs(cc.y, cc.x, cr.x, up.y, nc.y, A.k, A.rX, A.rY);
-                if(fast)
+                uint32_t const gj = y0 + r0 + r;
+                bool const rowInside = gj >= 1 && gj <= A.ny && gj >= W.j0 && gj < W.j1;
+                if(colsInside && rowInside)
                 {
                     stg2<HINT>(out, v0, v1);
+                    if(W.strip)
+                    {
+                        // fused halo exchange, row part: this row is the neighbour's ghost row
+                        if(gj == 1u && A.peerDst[0] != nullptr)
+                            stg2<0>(A.peerDst[0] + size_t(A.ny + 1u) * A.pitchElems + gi, v0, v1);
+                        if(gj == A.ny && A.peerDst[1] != nullptr)
+                            stg2<0>(A.peerDst[1] + gi, v0, v1);
+                    }
                 }
                 else
                 {
-                    uint32_t const gj = y0 + r0 + r;
                     bool w0 = false, w1 = false;
                     bool core0 = false, core1 = false;
                     double o0 = v0, o1 = v1;
@@ -322,29 +333,26 @@ namespace
                         out[0] = o0;
                     else if(w1)
                         out[1] = o1;
-                    if(W.strip)
+                    if(W.strip && (core0 || core1))
                     {
                         // fused halo exchange: the border cells of this tile are the neighbours' ghost cells. Peer stores
                         // (NVLink) straight from the registers that hold the fresh values; tiles have equal extents, so
                         // the neighbour's padded coordinates mirror ours.
-                        if(core0 || core1)
+                        if(gj == 1u && A.peerDst[0] != nullptr)
                         {
-                            if(gj == 1u && A.peerDst[0] != nullptr)
-                            {
-                                double* row = A.peerDst[0] + size_t(A.ny + 1u) * A.pitchElems + gi;
-                                if(core0)
-                                    row[0] = v0;
-                                if(core1)
-                                    row[1] = v1;
-                            }
-                            if(gj == A.ny && A.peerDst[1] != nullptr)
-                            {
-                                double* row = A.peerDst[1] + gi;
-                                if(core0)
-                                    row[0] = v0;
-                                if(core1)
-                                    row[1] = v1;
-                            }
+                            double* row = A.peerDst[0] + size_t(A.ny + 1u) * A.pitchElems + gi;
+                            if(core0)
+                                row[0] = v0;
+                            if(core1)
+                                row[1] = v1;
+                        }
+                        if(gj == A.ny && A.peerDst[1] != nullptr)
+                        {
+                            double* row = A.peerDst[1] + gi;
+                            if(core0)
+                                row[0] = v0;
+                            if(core1)
+                                row[1] = v1;
                         }
                         if(core1 && gi + 1u == 1u && A.peerDst[2] != nullptr)
                             A.peerDst[2][size_t(gj) * A.pitchElems + A.nx + 1u] = v1;
@@ -626,7 +634,10 @@ extern "C"
             A.sx = plan->sx;
             A.sy = plan->sy;
             A.edges = plan->edges;
-            int stages = int(b200::tune("heat.stages", 2));
+            // heat.ctas_per_sm = 0 (default): ONE tile per CTA, a single stage, residency (6 CTAs of 288 threads per SM)
+            // hides the latency. > 0: persistent CTAs striding over the tiles with a `heat.stages`-deep TMA ring.
+            bool const persistent = b200::tune("heat.ctas_per_sm", 0) > 0;
+            int stages = int(b200::tune("heat.stages", persistent ? 2 : 1));
             A.stages = stages < 1 ? 1 : (stages > kMaxStages ? kMaxStages : stages);
             return A;
         }
@@ -635,9 +646,9 @@ extern "C"
         {
             if(A.totalTiles == 0)
                 return 0;
-            int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 1));
+            int const ctasPerSm = int(b200::tune("heat.ctas_per_sm", 0));
             int const hint = int(b200::tune("heat.hint", 1));
-            uint64_t grid = uint64_t(b200::smCount(plan->dev)) * (ctasPerSm > 0 ? ctasPerSm : 1);
+            uint64_t grid = ctasPerSm > 0 ? uint64_t(b200::smCount(plan->dev)) * ctasPerSm : uint64_t(A.totalTiles);
             // heat.grid_cap: upper bound on CTAs per launch. Needed when several decomposed tiles share ONE device
             // (tests): their kernels wait for each other's flags, so all of them must be resident at the same time.
             int64_t const cap = b200::tune("heat.grid_cap", 0);
@@ -647,7 +658,7 @@ extern "C"
                 grid = A.totalTiles;
             auto const s = reinterpret_cast<cudaStream_t>(stream);
             size_t const smemBytes = size_t(A.stages) * STAGE_BYTES;
-            int const rpt = int(b200::tune("heat.rpt", 4));
+            int const rpt = int(b200::tune("heat.rpt", 8));
             auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map[src_index], A); };
             switch(rpt * 2 + (hint ? 1 : 0))
             {

@@ -8,7 +8,11 @@
 //     all loads of an iteration issued before the first store;
 //   * a block owns a contiguous chunk of blockDim*UNROLL vectors per iteration, a warp access is one
 //     contiguous 512 B / 1 KiB span (fully coalesced, 4 or 8 sectors per request per thread);
-//   * grid = SMs x ctas_per_sm persistent blocks striding over chunks (or one block per chunk);
+//   * grid: ONE block per chunk by default (stream.ctas_per_sm = 0). Measured on B200 at 2^30 doubles
+//     (tools/tune.py stream, profiles/r01/tune_stream.log): one-chunk blocks reach 7.0-7.1 TB/s for Copy/Mul/Triad and
+//     7.6 TB/s for Init, a persistent grid of SMs x {2,4,8} blocks striding over the chunks only 6.1-6.7 TB/s -- the
+//     hardware block scheduler spreads the DRAM pages touched at any instant better than lock-step strides do;
+//     stream.ctas_per_sm > 0 selects the persistent form;
 //   * streaming cache policy (ld.global.nc.L1::no_allocate, st.global.cs) because nothing is re-used;
 //   * arithmetic is __dmul_rn/__dadd_rn (__fmul_rn/__fadd_rn): FMA contraction pinned OFF so the bits equal the
 //     reference CPU back-end compiled with -ffp-contract=off.
@@ -31,6 +35,13 @@ namespace
         T v[N];
     };
 
+    // HINT: 0 = default cache policy, 1 = streaming loads (ld.nc.L1::no_allocate) AND streaming stores (st.cs),
+    //       2 = streaming loads only, 3 = streaming stores only
+    template<int HINT>
+    inline constexpr int kLoadHint = (HINT == 1 || HINT == 2) ? 1 : 0;
+    template<int HINT>
+    inline constexpr int kStoreHint = (HINT == 1 || HINT == 3) ? 1 : 0;
+
     template<int HINT, typename T, int VB>
     __device__ __forceinline__ Pack<T, VB> loadPack(T const* base, uint64_t vecIdx)
     {
@@ -39,13 +50,13 @@ namespace
         if constexpr(VB == 32)
         {
             uint64_t r[4];
-            ldg256<HINT>(ptr, r);
+            ldg256<kLoadHint<HINT>>(ptr, r);
             memcpy(p.v, r, 32);
         }
         else if constexpr(VB == 16)
         {
             uint32_t r[4];
-            ldg128<HINT>(ptr, r);
+            ldg128<kLoadHint<HINT>>(ptr, r);
             memcpy(p.v, r, 16);
         }
         else
@@ -64,13 +75,13 @@ namespace
         {
             uint64_t r[4];
             memcpy(r, p.v, 32);
-            stg256<HINT>(ptr, r);
+            stg256<kStoreHint<HINT>>(ptr, r);
         }
         else if constexpr(VB == 16)
         {
             uint32_t r[4];
             memcpy(r, p.v, 16);
-            stg128<HINT>(ptr, r);
+            stg128<kStoreHint<HINT>>(ptr, r);
         }
         else
         {
@@ -336,10 +347,10 @@ namespace
         StreamCfg c;
         std::string const p = std::string("stream.") + opName + ".";
         c.vb = int(b200::tune((p + "vb").c_str(), b200::tune("stream.vb", 32)));
-        c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", 2)));
+        c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", 1)));
         c.hint = int(b200::tune((p + "hint").c_str(), b200::tune("stream.hint", 1)));
         c.block = int(b200::tune((p + "block").c_str(), b200::tune("stream.block", 512)));
-        c.ctasPerSm = int(b200::tune((p + "ctas_per_sm").c_str(), b200::tune("stream.ctas_per_sm", 4)));
+        c.ctasPerSm = int(b200::tune((p + "ctas_per_sm").c_str(), b200::tune("stream.ctas_per_sm", 0)));
         return c;
     }
 
@@ -393,8 +404,22 @@ namespace
             vb = 16;
         if(vb == 16 && !aligned16)
             vb = int(sizeof(T));
+        if(cfg.hint < 0 || cfg.hint > 3)
+            return b200::fail(B200_EINVAL, "stream.hint must be 0..3", __FILE__, __LINE__);
         if(vb == 32)
-            return cfg.hint ? launchUnroll<Op, T, 32, 1>(s, op, n, cfg) : launchUnroll<Op, T, 32, 0>(s, op, n, cfg);
+        {
+            switch(cfg.hint)
+            {
+            case 0:
+                return launchUnroll<Op, T, 32, 0>(s, op, n, cfg);
+            case 1:
+                return launchUnroll<Op, T, 32, 1>(s, op, n, cfg);
+            case 2:
+                return launchUnroll<Op, T, 32, 2>(s, op, n, cfg);
+            default:
+                return launchUnroll<Op, T, 32, 3>(s, op, n, cfg);
+            }
+        }
         if(vb == 16)
             return cfg.hint ? launchUnroll<Op, T, 16, 1>(s, op, n, cfg) : launchUnroll<Op, T, 16, 0>(s, op, n, cfg);
         // element-aligned only: scalar path (still on the GPU; there is no CPU fallback)

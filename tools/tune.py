@@ -72,7 +72,7 @@ def sweep_stream(args, dev, q):
     names = args.kernels.split(",") if args.kernels else ["triad", "copy"]
     for name in names:
         fn, bpe = runs[name]
-        for vb, unroll, hint, block, ctas in itertools.product((32, 16), (1, 2, 4), (0, 1), (256, 512), (0, 2, 4, 8)):
+        for vb, unroll, hint, block, ctas in itertools.product((32,), (1, 2, 4), (0, 1, 2, 3), (256, 512), (0, 2, 4, 8)):
             if block * ctas > 2048:
                 continue
             for k, v in (("vb", vb), ("unroll", unroll), ("hint", hint), ("block", block), ("ctas_per_sm", ctas)):
