@@ -777,6 +777,13 @@ extern "C"
             A.peerFlag[side] = plan->halo.peer_flag[side];
         }
         A.myFlags = plan->halo.my_flags;
+        // heat.halo_debug (measurement only, results become wrong): 1 = no peer stores, 2 = no flag wait
+        int64_t const dbg = b200::tune("heat.halo_debug", 0);
+        if(dbg & 1)
+            for(int side = 0; side < 4; ++side)
+                A.peerDst[side] = nullptr;
+        if(dbg & 2)
+            A.myFlags = nullptr;
         A.stripCounter = plan->haloScratch;
         A.status = plan->haloScratch + 1;
         A.step = step;

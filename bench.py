@@ -373,6 +373,22 @@ def run_ours(args):
             assert err < 1e-4, f"decomposed heat field deviates from the analytic solution: {err}"
             kernels["heat2d_f64"]["max_abs_error_vs_analytic"] = err
             runner.close()
+            if not args.heat:
+                # BASELINE.json configs[4]: 65536^2 weak-scaled over 8 GPUs = 16384 x 32768 core cells per GPU; the same
+                # per-GPU tile at other N (halo/interior overlap stress: 2 x 4.3 GB of state per GPU)
+                py, px = decomp.process_grid(world)
+                NYw, NXw = 16384 * py, 32768 * px
+                tile_w = decomp.tile_for(rank, world, NYw, NXw)
+                rw = multi.HeatTile(q, tile_w, NYw, NXw)
+                multi.connect_over_process_group(rw, dist)
+                rw.upload(rw.initial_field())
+                barrier()
+                ms_w = timed(lambda: rw.step(1), max(20, K), 5)
+                assert rw.status() == 0, "heat halo flag wait timed out"
+                record("heat2d_f64_weak", ms_w, 16.0 * NYw * NXw / world)
+                kernels["heat2d_f64_weak"]["scaling"] = "weak"
+                kernels["heat2d_f64_weak"]["decomposition"] = f"{NYw}x{NXw} global, {py}x{px} tiles of {tile_w.ny}x{tile_w.nx}"
+                rw.close()
         q.wait()
 
     # ---- e2e: Triad through the public host API, pinned HOST buffers, copies inside the timed region

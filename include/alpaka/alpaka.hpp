@@ -21,3 +21,4 @@
 #include "b200/Kernel.hpp"
 #include "b200/Native.hpp"
 #include "b200/Heat2D.hpp"
+#include "b200/Meta.hpp"

@@ -22,6 +22,11 @@
 
 namespace alpaka
 {
+    //! Size of the dynamic shared-memory arena of the reference's CPU accelerators
+    //! (block/shared/dyn/BlockSharedDynMemberAllocKiB.hpp). There is no such arena here; the name exists because code
+    //! written against the reference mentions it inside `if constexpr` branches for CPU tags.
+    inline constexpr std::uint32_t BlockSharedDynMemberAllocKiB = 47u;
+
     //! The vendor-API tag of this back-end (the reference's slot for ApiCudaRt / ApiHipRt).
     struct ApiB200Rt
     {
@@ -180,6 +185,25 @@ namespace alpaka
             }
         };
     } // namespace trait
+
+    namespace core
+    {
+        namespace detail
+        {
+            template<typename T>
+            inline auto demangle() -> std::string
+            {
+                int status = 0;
+                char* dm = abi::__cxa_demangle(typeid(T).name(), nullptr, nullptr, &status);
+                std::string const r = (status == 0 && dm != nullptr) ? dm : typeid(T).name();
+                std::free(dm);
+                return r;
+            }
+        } // namespace detail
+        //! human-readable name of T (reference: core/DemangleTypeNames.hpp)
+        template<typename T>
+        inline std::string const demangled = detail::demangle<T>();
+    } // namespace core
 
     template<typename TAcc>
     using Acc = typename trait::AccType<TAcc>::type;
@@ -589,7 +613,7 @@ namespace alpaka
         {
             static_assert(sizeof(TTo) == sizeof(TFrom));
             TTo r;
-            memcpy(&r, &v, sizeof(TTo));
+            ::memcpy(&r, &v, sizeof(TTo));
             return r;
         }
 

@@ -58,6 +58,72 @@
 
 #define ALPAKA_FN_EXTERN extern
 
+// Compiler/language identification in the Boost.Predef vocabulary the reference (and code written against it) tests
+// with `#if BOOST_COMP_NVCC` etc. (core/BoostPredef.hpp). Boost itself is not a dependency here: only these names,
+// with Boost's value encoding (major * 10'000'000 + minor * 100'000 + patch, 0 = not this compiler).
+#ifndef BOOST_VERSION_NUMBER
+#    define BOOST_VERSION_NUMBER(major, minor, patch)                                                                \
+        ((((major) % 100) * 10000000) + (((minor) % 100) * 100000) + ((patch) % 100000))
+#    define BOOST_VERSION_NUMBER_NOT_AVAILABLE 0
+#    define BOOST_VERSION_NUMBER_AVAILABLE BOOST_VERSION_NUMBER(0, 0, 1)
+#endif
+#ifndef BOOST_LANG_CUDA
+#    if defined(__CUDACC__)
+#        define BOOST_LANG_CUDA BOOST_VERSION_NUMBER(__CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, __CUDACC_VER_BUILD__)
+#    else
+#        define BOOST_LANG_CUDA BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#    endif
+#endif
+#ifndef BOOST_LANG_HIP
+#    define BOOST_LANG_HIP BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_COMP_NVCC
+#    if defined(__NVCC__)
+#        define BOOST_COMP_NVCC BOOST_VERSION_NUMBER(__CUDACC_VER_MAJOR__, __CUDACC_VER_MINOR__, __CUDACC_VER_BUILD__)
+#    else
+#        define BOOST_COMP_NVCC BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#    endif
+#endif
+#ifndef BOOST_COMP_GNUC
+#    if defined(__GNUC__) && !defined(__clang__)
+#        define BOOST_COMP_GNUC BOOST_VERSION_NUMBER(__GNUC__, __GNUC_MINOR__, __GNUC_PATCHLEVEL__)
+#    else
+#        define BOOST_COMP_GNUC BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#    endif
+#endif
+#ifndef BOOST_COMP_CLANG
+#    if defined(__clang__)
+#        define BOOST_COMP_CLANG BOOST_VERSION_NUMBER(__clang_major__, __clang_minor__, __clang_patchlevel__)
+#    else
+#        define BOOST_COMP_CLANG BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#    endif
+#endif
+#ifndef BOOST_COMP_CLANG_CUDA
+#    define BOOST_COMP_CLANG_CUDA BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_COMP_MSVC
+#    define BOOST_COMP_MSVC BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_COMP_MSVC_EMULATED
+#    define BOOST_COMP_MSVC_EMULATED BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_COMP_PGI
+#    define BOOST_COMP_PGI BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_COMP_HIP
+#    define BOOST_COMP_HIP BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+#ifndef BOOST_ARCH_PTX
+#    if defined(__CUDA_ARCH__)
+#        define BOOST_ARCH_PTX BOOST_VERSION_NUMBER(__CUDA_ARCH__ / 100, (__CUDA_ARCH__ % 100) / 10, 0)
+#    else
+#        define BOOST_ARCH_PTX BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#    endif
+#endif
+#ifndef BOOST_ARCH_HSA
+#    define BOOST_ARCH_HSA BOOST_VERSION_NUMBER_NOT_AVAILABLE
+#endif
+
 // ALPAKA_UNROLL(n) / ALPAKA_UNROLL(): loop unrolling hint placed in front of a loop.
 #define ALPAKA_B200_PRAGMA(x) _Pragma(#x)
 #if defined(__CUDACC__)

@@ -439,6 +439,136 @@ namespace alpaka
             I)
 #undef ALPAKA_B200_VIEW_TRAITS
 
+        // ---- std::vector and std::array are 1-D host views (reference: mem/view/ViewStdVector.hpp, ViewStdArray.hpp)
+        template<typename TElem, typename TAlloc>
+        struct DevType<std::vector<TElem, TAlloc>>
+        {
+            using type = DevCpu;
+        };
+        template<typename TElem, typename TAlloc>
+        struct DimType<std::vector<TElem, TAlloc>>
+        {
+            using type = DimInt<1u>;
+        };
+        template<typename TElem, typename TAlloc>
+        struct IdxType<std::vector<TElem, TAlloc>>
+        {
+            using type = std::size_t;
+        };
+        template<typename TElem, typename TAlloc>
+        struct ElemType<std::vector<TElem, TAlloc>>
+        {
+            using type = TElem;
+        };
+        template<typename TElem, typename TAlloc>
+        struct GetDev<std::vector<TElem, TAlloc>>
+        {
+            static auto getDev(std::vector<TElem, TAlloc> const&) -> DevCpu
+            {
+                return DevCpu{};
+            }
+        };
+        template<typename TElem, typename TAlloc>
+        struct GetExtents<std::vector<TElem, TAlloc>>
+        {
+            auto operator()(std::vector<TElem, TAlloc> const& v) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{v.size()};
+            }
+        };
+        template<typename TElem, typename TAlloc>
+        struct GetOffsets<std::vector<TElem, TAlloc>>
+        {
+            auto operator()(std::vector<TElem, TAlloc> const&) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{std::size_t{0}};
+            }
+        };
+        template<typename TElem, typename TAlloc>
+        struct GetPtrNative<std::vector<TElem, TAlloc>>
+        {
+            static auto getPtrNative(std::vector<TElem, TAlloc> const& v) -> TElem const*
+            {
+                return v.data();
+            }
+            static auto getPtrNative(std::vector<TElem, TAlloc>& v) -> TElem*
+            {
+                return v.data();
+            }
+        };
+        template<typename TElem, typename TAlloc>
+        struct GetPitchesInBytes<std::vector<TElem, TAlloc>>
+        {
+            auto operator()(std::vector<TElem, TAlloc> const&) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{sizeof(TElem)};
+            }
+        };
+        template<typename TElem, std::size_t N>
+        struct DevType<std::array<TElem, N>>
+        {
+            using type = DevCpu;
+        };
+        template<typename TElem, std::size_t N>
+        struct DimType<std::array<TElem, N>>
+        {
+            using type = DimInt<1u>;
+        };
+        template<typename TElem, std::size_t N>
+        struct IdxType<std::array<TElem, N>>
+        {
+            using type = std::size_t;
+        };
+        template<typename TElem, std::size_t N>
+        struct ElemType<std::array<TElem, N>>
+        {
+            using type = TElem;
+        };
+        template<typename TElem, std::size_t N>
+        struct GetDev<std::array<TElem, N>>
+        {
+            static auto getDev(std::array<TElem, N> const&) -> DevCpu
+            {
+                return DevCpu{};
+            }
+        };
+        template<typename TElem, std::size_t N>
+        struct GetExtents<std::array<TElem, N>>
+        {
+            auto operator()(std::array<TElem, N> const&) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{N};
+            }
+        };
+        template<typename TElem, std::size_t N>
+        struct GetOffsets<std::array<TElem, N>>
+        {
+            auto operator()(std::array<TElem, N> const&) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{std::size_t{0}};
+            }
+        };
+        template<typename TElem, std::size_t N>
+        struct GetPtrNative<std::array<TElem, N>>
+        {
+            static auto getPtrNative(std::array<TElem, N> const& v) -> TElem const*
+            {
+                return v.data();
+            }
+            static auto getPtrNative(std::array<TElem, N>& v) -> TElem*
+            {
+                return v.data();
+            }
+        };
+        template<typename TElem, std::size_t N>
+        struct GetPitchesInBytes<std::array<TElem, N>>
+        {
+            auto operator()(std::array<TElem, N> const&) const -> Vec<DimInt<1u>, std::size_t>
+            {
+                return Vec<DimInt<1u>, std::size_t>{sizeof(TElem)};
+            }
+        };
+
         template<typename V, typename E, typename D, typename I>
         struct GetOffsets<ViewSubView<V, E, D, I>>
         {

@@ -552,6 +552,13 @@ namespace alpaka
             return Vec<DimInt<sizeof...(Is)>, TVal>{v[Is]...};
     }
 
+    //! the same with the sequence as explicit template argument: subVecFromIndices<std::index_sequence<0, 2>>(v)
+    template<typename TIndexSequence, typename TDim, typename TVal>
+    [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto subVecFromIndices(Vec<TDim, TVal> const& v)
+    {
+        return subVecFromIndices(v, TIndexSequence{});
+    }
+
     namespace detail
     {
         template<std::size_t Off, std::size_t... Is>
@@ -591,22 +598,33 @@ namespace alpaka
         return r;
     }
 
-    template<typename TDim, typename TVal>
-    [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto elementwise_min(Vec<TDim, TVal> const& a, Vec<TDim, TVal> const& b)
+    //! component-wise minimum / maximum of one or more vectors
+    template<typename TDim, typename TVal, typename... TVecs>
+    [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto elementwise_min(Vec<TDim, TVal> const& first, TVecs const&... rest)
         -> Vec<TDim, TVal>
     {
-        Vec<TDim, TVal> r;
-        for(std::size_t i = 0; i < TDim::value; ++i)
-            r[i] = a[i] < b[i] ? a[i] : b[i];
+        static_assert((std::is_same_v<Vec<TDim, TVal>, TVecs> && ...), "elementwise_min: all vectors must have one type");
+        Vec<TDim, TVal> r = first;
+        auto const fold = [&r](Vec<TDim, TVal> const& v)
+        {
+            for(std::size_t i = 0; i < TDim::value; ++i)
+                r[i] = v[i] < r[i] ? v[i] : r[i];
+        };
+        (fold(rest), ...);
         return r;
     }
-    template<typename TDim, typename TVal>
-    [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto elementwise_max(Vec<TDim, TVal> const& a, Vec<TDim, TVal> const& b)
+    template<typename TDim, typename TVal, typename... TVecs>
+    [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto elementwise_max(Vec<TDim, TVal> const& first, TVecs const&... rest)
         -> Vec<TDim, TVal>
     {
-        Vec<TDim, TVal> r;
-        for(std::size_t i = 0; i < TDim::value; ++i)
-            r[i] = a[i] > b[i] ? a[i] : b[i];
+        static_assert((std::is_same_v<Vec<TDim, TVal>, TVecs> && ...), "elementwise_max: all vectors must have one type");
+        Vec<TDim, TVal> r = first;
+        auto const fold = [&r](Vec<TDim, TVal> const& v)
+        {
+            for(std::size_t i = 0; i < TDim::value; ++i)
+                r[i] = v[i] > r[i] ? v[i] : r[i];
+        };
+        (fold(rest), ...);
         return r;
     }
 

@@ -20,18 +20,18 @@ namespace alpaka
     public:
         ALPAKA_FN_HOST_ACC WorkDivMembers() = delete;
 
-        //! accepts Vecs and, for 1-D, plain scalars (reference: workdiv/WorkDivMembers.hpp:26-35)
+        //! Accepts anything with extents -- Vecs, user vector types with a trait::GetExtents, plain scalars for 1-D --
+        //! of TDim or MORE dimensions; extra (slowest) dimensions are dropped
+        //! (reference: workdiv/WorkDivMembers.hpp:26-35, test/unit/workDiv/src/WorkDivHelpersTest.cpp:223-249).
         template<typename TGridBlockExtent, typename TBlockThreadExtent, typename TThreadElemExtent>
         ALPAKA_FN_HOST_ACC explicit WorkDivMembers(
             TGridBlockExtent const& gridBlockExtent = TGridBlockExtent(),
             TBlockThreadExtent const& blockThreadExtent = TBlockThreadExtent(),
             TThreadElemExtent const& threadElemExtent = TThreadElemExtent())
-            : m_gridBlockExtent(castVec<TIdx>(getExtents(gridBlockExtent)))
-            , m_blockThreadExtent(castVec<TIdx>(getExtents(blockThreadExtent)))
-            , m_threadElemExtent(castVec<TIdx>(getExtents(threadElemExtent)))
+            : m_gridBlockExtent(subVecEnd<TDim>(castVec<TIdx>(getExtents(gridBlockExtent))))
+            , m_blockThreadExtent(subVecEnd<TDim>(castVec<TIdx>(getExtents(blockThreadExtent))))
+            , m_threadElemExtent(subVecEnd<TDim>(castVec<TIdx>(getExtents(threadElemExtent))))
         {
-            static_assert(Dim<TGridBlockExtent>::value == TDim::value && Dim<TBlockThreadExtent>::value == TDim::value
-                          && Dim<TThreadElemExtent>::value == TDim::value);
         }
 
         //! braced lists: WorkDivMembers<Dim,Idx>{{2,2}, {16,16}, {1,1}}
