@@ -694,6 +694,59 @@ extern "C"
         return 0;
     }
 
+    int b200_symbol_address(int dev, void const* symbol, void** out)
+    {
+        B200_REQUIRE(symbol && out, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(dev));
+        B200_CUDA(cudaGetSymbolAddress(out, symbol));
+        return 0;
+    }
+
+    // ------------------------------------------------------------------ stream memory operations
+    namespace
+    {
+        // CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned flags); 0 == CUDA_SUCCESS
+        using StreamValue32Fn = int (*)(cudaStream_t, unsigned long long, uint32_t, unsigned);
+
+        StreamValue32Fn driverEntry(char const* name)
+        {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult status = cudaDriverEntryPointSymbolNotFound;
+            if(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &status) != cudaSuccess
+               || status != cudaDriverEntryPointSuccess)
+            {
+                (void) cudaGetLastError();
+                return nullptr;
+            }
+            return reinterpret_cast<StreamValue32Fn>(fn);
+        }
+    } // namespace
+
+    int b200_stream_wait_value32(int dev, b200_stream_t s, void* addr, uint32_t value)
+    {
+        B200_REQUIRE(addr, B200_EINVAL);
+        B200_REQUIRE((reinterpret_cast<uintptr_t>(addr) & 3u) == 0, B200_EALIGN);
+        B200_CUDA(cudaSetDevice(dev));
+        static StreamValue32Fn const fn = driverEntry("cuStreamWaitValue32");
+        B200_REQUIRE(fn, B200_ENODEV);
+        constexpr unsigned waitGeq = 0x0; // CU_STREAM_WAIT_VALUE_GEQ
+        int const rc = fn(cs(s), static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(addr)), value, waitGeq);
+        B200_REQUIRE(rc == 0, B200_ENODEV);
+        return 0;
+    }
+
+    int b200_stream_write_value32(int dev, b200_stream_t s, void* addr, uint32_t value)
+    {
+        B200_REQUIRE(addr, B200_EINVAL);
+        B200_REQUIRE((reinterpret_cast<uintptr_t>(addr) & 3u) == 0, B200_EALIGN);
+        B200_CUDA(cudaSetDevice(dev));
+        static StreamValue32Fn const fn = driverEntry("cuStreamWriteValue32");
+        B200_REQUIRE(fn, B200_ENODEV);
+        int const rc = fn(cs(s), static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(addr)), value, 0u);
+        B200_REQUIRE(rc == 0, B200_ENODEV);
+        return 0;
+    }
+
     // ------------------------------------------------------------------ tuning / introspection
     int b200_tune_set(char const* key, int64_t value)
     {

@@ -10,6 +10,8 @@
 #include <cassert>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
+#include <stdexcept>
 
 #define ALPAKA_VERSION_MAJOR 2
 #define ALPAKA_VERSION_MINOR 0
@@ -42,12 +44,24 @@
 #    else
 #        define ALPAKA_NO_HOST_ACC_WARNING
 #    endif
-#    define ALPAKA_STATIC_ACC_MEM_GLOBAL                                                                              \
-        template<typename TAccTagB200 = void>                                                                        \
-        inline __device__
-#    define ALPAKA_STATIC_ACC_MEM_CONSTANT                                                                            \
-        template<typename TAccTagB200 = void>                                                                        \
-        inline __constant__
+// Device-global variable templates (see Global.hpp). The template parameter is spelled TAcc because user code names
+// it inside the declaration: `ALPAKA_STATIC_ACC_MEM_GLOBAL alpaka::DevGlobal<TAcc, int> g;` (reference:
+// core/Common.hpp:136-206). Without relocatable device code CUDA requires internal linkage for such variables.
+#    if defined(__CUDACC_RDC__)
+#        define ALPAKA_STATIC_ACC_MEM_GLOBAL                                                                          \
+            template<typename TAcc>                                                                                   \
+            __device__ inline
+#        define ALPAKA_STATIC_ACC_MEM_CONSTANT                                                                        \
+            template<typename TAcc>                                                                                   \
+            __constant__ inline
+#    else
+#        define ALPAKA_STATIC_ACC_MEM_GLOBAL                                                                          \
+            template<typename TAcc>                                                                                   \
+            __device__ static
+#        define ALPAKA_STATIC_ACC_MEM_CONSTANT                                                                        \
+            template<typename TAcc>                                                                                   \
+            __constant__ static
+#    endif
 #else
 #    define ALPAKA_FN_ACC
 #    define ALPAKA_FN_HOST_ACC
@@ -147,6 +161,23 @@
 #endif
 
 #define ALPAKA_DEVICE_VOLATILE volatile
+
+// ALPAKA_THROW_ACC(msg): user-defined fatal error inside a kernel (reference: core/RuntimeMacros.hpp:21-51). On the
+// device it prints the message and traps; the host sees cudaErrorLaunchFailure as std::runtime_error at the next
+// wait(). In host code it throws std::runtime_error directly.
+#if defined(__CUDA_ARCH__)
+#    define ALPAKA_THROW_ACC(MSG)                                                                                     \
+        {                                                                                                             \
+            printf("alpaka encountered a user-defined error condition while running on the B200 back-end:\n%s", (MSG)); \
+            __trap();                                                                                                 \
+        }
+#else
+#    define ALPAKA_THROW_ACC(MSG)                                                                                     \
+        {                                                                                                             \
+            printf("alpaka encountered a user-defined error condition:\n%s", (MSG));                                  \
+            throw std::runtime_error(MSG);                                                                            \
+        }
+#endif
 
 // scope logging of the reference (core/Debug.hpp) is a no-op unless ALPAKA_DEBUG >= 2
 #if ALPAKA_DEBUG >= ALPAKA_DEBUG_FULL

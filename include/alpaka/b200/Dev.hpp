@@ -15,8 +15,11 @@
 #include "Tags.hpp"
 #include "b200/b200.h"
 
+#include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <fstream>
 #include <functional>
 #include <future>
@@ -111,12 +114,221 @@ namespace alpaka
 
     namespace b200
     {
-        //! host task queue: tasks run inline on the calling thread, serialised by a mutex
-        //! (reference: queue/QueueGenericThreadsBlocking.hpp:127-163)
+        //! A single worker thread that runs `void()` tasks in submission order. Used by non-blocking host queues and by
+        //! device queues for host tasks (a CUDA host-function callback must not call the runtime; reference:
+        //! core/CallbackThread.hpp + queue/cuda_hip/QueueUniformCudaHipRt.hpp:194-230). A task object is destroyed
+        //! BEFORE its completion is published, so "wait(queue) returned" implies "the task's captures are gone"
+        //! (reference test: QueueTest.cpp "taskIsDestroyedAfterExecution"). The destructor drains the backlog.
+        class CallbackThread
+        {
+            struct Item
+            {
+                std::function<void()> fn;
+                std::promise<void> done;
+            };
+
+        public:
+            CallbackThread() = default;
+            CallbackThread(CallbackThread const&) = delete;
+            auto operator=(CallbackThread const&) -> CallbackThread& = delete;
+            ~CallbackThread()
+            {
+                {
+                    std::lock_guard<std::mutex> l(m_mutex);
+                    m_stop = true;
+                }
+                m_cv.notify_all();
+                if(m_thread.joinable())
+                {
+                    if(m_thread.get_id() == std::this_thread::get_id())
+                        m_thread.detach(); // the last handle died inside one of our own tasks
+                    else
+                        m_thread.join();
+                }
+            }
+
+            auto submit(std::function<void()> fn) -> std::shared_future<void>
+            {
+                Item item{std::move(fn), {}};
+                std::shared_future<void> fut = item.done.get_future().share();
+                {
+                    std::lock_guard<std::mutex> l(m_mutex);
+                    ++m_pending;
+                    m_items.emplace_back(std::move(item));
+                    if(!m_thread.joinable())
+                        m_thread = std::thread([this] { run(); });
+                }
+                m_cv.notify_one();
+                return fut;
+            }
+
+            //! number of tasks submitted and not yet finished (the running one included)
+            [[nodiscard]] auto pending() const -> std::size_t
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                return m_pending;
+            }
+
+            //! true when called from inside one of this thread's tasks
+            [[nodiscard]] auto onWorker() const -> bool
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                return m_thread.joinable() && m_thread.get_id() == std::this_thread::get_id();
+            }
+
+        private:
+            void run()
+            {
+                for(;;)
+                {
+                    Item item;
+                    {
+                        std::unique_lock<std::mutex> l(m_mutex);
+                        m_cv.wait(l, [this] { return m_stop || !m_items.empty(); });
+                        if(m_items.empty())
+                            return;
+                        item = std::move(m_items.front());
+                        m_items.pop_front();
+                    }
+                    std::exception_ptr error;
+                    try
+                    {
+                        item.fn();
+                    }
+                    catch(...)
+                    {
+                        error = std::current_exception();
+                    }
+                    item.fn = nullptr; // destroy the task (and what it captured) before anybody is told it finished
+                    {
+                        std::lock_guard<std::mutex> l(m_mutex);
+                        --m_pending;
+                    }
+                    if(error)
+                        item.done.set_exception(error);
+                    else
+                        item.done.set_value();
+                }
+            }
+
+            mutable std::mutex m_mutex;
+            std::condition_variable m_cv;
+            std::deque<Item> m_items;
+            std::thread m_thread;
+            std::size_t m_pending = 0;
+            bool m_stop = false;
+        };
+
+        //! One recording of a host event: signalled once, when the queue it was enqueued into reaches it.
+        class HostMarker
+        {
+        public:
+            void signal()
+            {
+                {
+                    std::lock_guard<std::mutex> l(m_mutex);
+                    m_done = true;
+                }
+                m_cv.notify_all();
+            }
+            void wait()
+            {
+                std::unique_lock<std::mutex> l(m_mutex);
+                m_cv.wait(l, [this] { return m_done; });
+            }
+            [[nodiscard]] auto done() const -> bool
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                return m_done;
+            }
+
+        private:
+            mutable std::mutex m_mutex;
+            std::condition_variable m_cv;
+            bool m_done = false;
+        };
+
+        //! Host task queue. Blocking: the task runs on the calling thread, serialised by a mutex
+        //! (reference: queue/QueueGenericThreadsBlocking.hpp:127-163). Non-blocking: the task is handed to the queue's
+        //! worker thread and the call returns (reference: queue/QueueGenericThreadsNonBlocking.hpp:100-140).
         class QueueCpuImpl
         {
         public:
+            explicit QueueCpuImpl(bool blocking) : m_blocking(blocking)
+            {
+            }
+
+            void run(std::function<void()> fn)
+            {
+                if(m_blocking)
+                {
+                    std::lock_guard<std::mutex> l(m_mutex);
+                    m_busy.store(true);
+                    struct Clear
+                    {
+                        std::atomic<bool>& b;
+                        ~Clear()
+                        {
+                            b.store(false);
+                        }
+                    } clear{m_busy};
+                    fn();
+                    fn = nullptr;
+                }
+                else
+                    (void) m_worker.submit(std::move(fn));
+            }
+
+            [[nodiscard]] auto empty() const -> bool
+            {
+                return m_blocking ? !m_busy.load() : m_worker.pending() == 0u;
+            }
+
+            //! returns once everything submitted before the call has finished
+            void drain()
+            {
+                if(m_blocking)
+                {
+                    std::lock_guard<std::mutex> l(m_mutex);
+                }
+                else if(!m_worker.onWorker())
+                    m_worker.submit([] {}).wait();
+            }
+
+            bool const m_blocking;
             std::mutex m_mutex;
+            std::atomic<bool> m_busy{false};
+            CallbackThread m_worker;
+        };
+
+        //! every live host queue, so that wait(DevCpu) can drain them (reference: dev/DevCpu.hpp queue registry)
+        class HostQueueRegistry
+        {
+        public:
+            static auto instance() -> HostQueueRegistry&
+            {
+                static HostQueueRegistry r;
+                return r;
+            }
+            void add(std::shared_ptr<QueueCpuImpl> const& q)
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                std::erase_if(m_queues, [](auto const& w) { return w.expired(); });
+                m_queues.emplace_back(q);
+            }
+            [[nodiscard]] auto snapshot() -> std::vector<std::shared_ptr<QueueCpuImpl>>
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                std::vector<std::shared_ptr<QueueCpuImpl>> live;
+                for(auto const& w : m_queues)
+                    if(auto sp = w.lock())
+                        live.emplace_back(std::move(sp));
+                return live;
+            }
+
+        private:
+            std::mutex m_mutex;
+            std::vector<std::weak_ptr<QueueCpuImpl>> m_queues;
         };
     } // namespace b200
 
@@ -124,8 +336,11 @@ namespace alpaka
     class QueueCpu
     {
     public:
-        explicit QueueCpu(DevCpu const& dev) : m_dev(dev), m_impl(std::make_shared<b200::QueueCpuImpl>())
+        explicit QueueCpu(DevCpu const& dev)
+            : m_dev(dev)
+            , m_impl(std::make_shared<b200::QueueCpuImpl>(std::is_same_v<TProperty, Blocking>))
         {
+            b200::HostQueueRegistry::instance().add(m_impl);
         }
         auto operator==(QueueCpu const& rhs) const -> bool
         {
@@ -183,61 +398,6 @@ namespace alpaka
 
     namespace b200
     {
-        //! runs host tasks enqueued into a device queue on its own thread, so that they may call the runtime
-        //! (a CUDA host-function callback must not). Reference: core/CallbackThread.hpp + QueueUniformCudaHipRt.hpp:194-230.
-        class CallbackThread
-        {
-        public:
-            ~CallbackThread()
-            {
-                {
-                    std::lock_guard<std::mutex> l(m_mutex);
-                    m_stop = true;
-                }
-                m_cv.notify_all();
-                if(m_thread.joinable())
-                    m_thread.join();
-            }
-
-            auto submit(std::function<void()> fn) -> std::future<void>
-            {
-                std::packaged_task<void()> task(std::move(fn));
-                auto fut = task.get_future();
-                {
-                    std::lock_guard<std::mutex> l(m_mutex);
-                    m_tasks.emplace_back(std::move(task));
-                    if(!m_thread.joinable())
-                        m_thread = std::thread([this] { run(); });
-                }
-                m_cv.notify_one();
-                return fut;
-            }
-
-        private:
-            void run()
-            {
-                for(;;)
-                {
-                    std::packaged_task<void()> task;
-                    {
-                        std::unique_lock<std::mutex> l(m_mutex);
-                        m_cv.wait(l, [this] { return m_stop || !m_tasks.empty(); });
-                        if(m_tasks.empty())
-                            return;
-                        task = std::move(m_tasks.front());
-                        m_tasks.pop_front();
-                    }
-                    task();
-                }
-            }
-
-            std::mutex m_mutex;
-            std::condition_variable m_cv;
-            std::deque<std::packaged_task<void()>> m_tasks;
-            std::thread m_thread;
-            bool m_stop = false;
-        };
-
         //! the stream behind a queue, plus the per-queue scratch used by the native single-pass reductions
         class QueueB200Impl
         {
@@ -358,18 +518,54 @@ namespace alpaka
     };
     using EventCudaRt = EventB200;
 
-    //! host event: complete as soon as it has been "recorded" (host queues run inline)
+    namespace b200
+    {
+        class EventCpuImpl
+        {
+        public:
+            explicit EventCpuImpl(DevCpu const& dev) : m_dev(dev)
+            {
+            }
+            //! the most recent recording (null: never enqueued)
+            [[nodiscard]] auto last() const -> std::shared_ptr<HostMarker>
+            {
+                std::lock_guard<std::mutex> l(m_mutex);
+                return m_last;
+            }
+            //! starts a new recording; earlier ones stay alive for whoever already waits on them
+            [[nodiscard]] auto record() -> std::shared_ptr<HostMarker>
+            {
+                auto marker = std::make_shared<HostMarker>();
+                std::lock_guard<std::mutex> l(m_mutex);
+                m_last = marker;
+                return marker;
+            }
+            DevCpu m_dev;
+
+        private:
+            mutable std::mutex m_mutex;
+            std::shared_ptr<HostMarker> m_last;
+        };
+    } // namespace b200
+
+    //! Host event with the semantics of a CUDA event: every enqueue is a new recording; isComplete / wait(event) look at
+    //! the latest recording, wait(queue, event) captures the recording that is current at the time of the call
+    //! (reference: event/EventGenericThreads.hpp:27-330, pinned by test/unit/event/src/EventTest.cpp).
     class EventCpu
     {
     public:
-        explicit EventCpu(DevCpu const& dev, bool = true) : m_dev(dev)
+        explicit EventCpu(DevCpu const& dev, bool = true) : m_impl(std::make_shared<b200::EventCpuImpl>(dev))
         {
         }
         auto operator==(EventCpu const& rhs) const -> bool
         {
-            return this == &rhs;
+            return m_impl == rhs.m_impl;
         }
-        DevCpu m_dev;
+        auto operator!=(EventCpu const& rhs) const -> bool
+        {
+            return !(*this == rhs);
+        }
+        std::shared_ptr<b200::EventCpuImpl> m_impl;
     };
 
     namespace b200
@@ -453,7 +649,7 @@ namespace alpaka
         {
             static auto getDev(EventCpu const& e) -> DevCpu
             {
-                return e.m_dev;
+                return e.m_impl->m_dev;
             }
         };
 
@@ -539,6 +735,10 @@ namespace alpaka
     {
         return t.getNativeHandle();
     }
+
+    //! the type getNativeHandle(T) returns (reference: traits/Traits.hpp:37-38)
+    template<typename T>
+    using NativeHandle = decltype(getNativeHandle(std::declval<T>()));
 
     // ---- platform
     [[nodiscard]] inline auto getDevCount(PlatformCpu const&) -> std::size_t
@@ -664,6 +864,8 @@ namespace alpaka
         {
             static void currentThreadWaitFor(DevCpu const&)
             {
+                for(auto const& q : b200::HostQueueRegistry::instance().snapshot())
+                    q->drain();
             }
         };
         template<typename TProperty>
@@ -671,14 +873,16 @@ namespace alpaka
         {
             static void currentThreadWaitFor(QueueCpu<TProperty> const& q)
             {
-                std::lock_guard<std::mutex> l(q.m_impl->m_mutex); // tasks run inline: holding the mutex = queue drained
+                q.m_impl->drain();
             }
         };
         template<>
         struct CurrentThreadWaitFor<EventCpu>
         {
-            static void currentThreadWaitFor(EventCpu const&)
+            static void currentThreadWaitFor(EventCpu const& e)
             {
+                if(auto const marker = e.m_impl->last())
+                    marker->wait();
             }
         };
         template<>
@@ -724,26 +928,41 @@ namespace alpaka
         template<typename TProperty>
         struct WaiterWaitFor<QueueCpu<TProperty>, EventCpu>
         {
-            static void waiterWaitFor(QueueCpu<TProperty>&, EventCpu const&)
+            static void waiterWaitFor(QueueCpu<TProperty>& q, EventCpu const& e)
             {
+                // the recording current NOW is the one to wait for, even if the event is re-enqueued later
+                auto const marker = e.m_impl->last();
+                if(marker && !marker->done())
+                    q.m_impl->run([marker] { marker->wait(); });
             }
         };
-        //! a host queue waiting for a device event blocks the calling thread (host tasks run inline)
+        template<>
+        struct WaiterWaitFor<DevCpu, EventCpu>
+        {
+            static void waiterWaitFor(DevCpu&, EventCpu const& e)
+            {
+                auto const marker = e.m_impl->last();
+                if(marker && !marker->done())
+                    for(auto const& q : b200::HostQueueRegistry::instance().snapshot())
+                        q->run([marker] { marker->wait(); });
+            }
+        };
+        //! a host queue waiting for a device event: the wait happens in queue order
         template<typename TProperty>
         struct WaiterWaitFor<QueueCpu<TProperty>, EventB200>
         {
-            static void waiterWaitFor(QueueCpu<TProperty>&, EventB200 const& e)
+            static void waiterWaitFor(QueueCpu<TProperty>& q, EventB200 const& e)
             {
-                b200::check(b200_event_sync(e.getNativeHandle()));
+                q.m_impl->run([e] { b200::check(b200_event_sync(e.getNativeHandle())); });
             }
         };
 
         template<typename TProperty>
         struct Empty<QueueCpu<TProperty>>
         {
-            static auto empty(QueueCpu<TProperty> const&) -> bool
+            static auto empty(QueueCpu<TProperty> const& q) -> bool
             {
-                return true;
+                return q.m_impl->empty();
             }
         };
         template<typename TProperty>
@@ -759,9 +978,10 @@ namespace alpaka
         template<>
         struct IsComplete<EventCpu>
         {
-            static auto isComplete(EventCpu const&) -> bool
+            static auto isComplete(EventCpu const& e) -> bool
             {
-                return true;
+                auto const marker = e.m_impl->last();
+                return !marker || marker->done();
             }
         };
         template<>
@@ -788,8 +1008,10 @@ namespace alpaka
         template<typename TProperty>
         struct Enqueue<QueueCpu<TProperty>, EventCpu>
         {
-            static void enqueue(QueueCpu<TProperty>&, EventCpu&)
+            static void enqueue(QueueCpu<TProperty>& q, EventCpu& e)
             {
+                auto marker = e.m_impl->record();
+                q.m_impl->run([marker] { marker->signal(); });
             }
         };
 
@@ -799,29 +1021,29 @@ namespace alpaka
         {
             static void enqueue(QueueCpu<TProperty>& q, TTask const& task)
             {
-                std::lock_guard<std::mutex> l(q.m_impl->m_mutex);
-                auto t = task;
-                t();
+                q.m_impl->run(std::function<void()>(task));
             }
         };
         template<typename TProperty, typename TTask>
         struct Enqueue<QueueB200<TProperty>, TTask, std::enable_if_t<std::is_invocable_v<TTask&>>>
         {
+            //! The queue is referenced, not owned: its destructor drains the stream (and with it this host function)
+            //! before anything is torn down, whereas owning it here could make the CUDA callback thread run that
+            //! destructor, where stream synchronisation is not permitted.
             struct Payload
             {
-                std::shared_ptr<b200::QueueB200Impl> impl; // keeps the callback thread alive
+                b200::QueueB200Impl* impl;
                 std::function<void()> fn;
             };
             static void trampoline(void* user)
             {
                 std::unique_ptr<Payload> p(static_cast<Payload*>(user));
                 // run on the queue's callback thread (it may call the runtime), block the stream until done
-                auto fut = p->impl->m_callbackThread.submit(std::move(p->fn));
-                fut.wait();
+                p->impl->m_callbackThread.submit(std::move(p->fn)).wait();
             }
             static void enqueue(QueueB200<TProperty>& q, TTask const& task)
             {
-                auto* p = new Payload{q.m_impl, std::function<void()>(task)};
+                auto* p = new Payload{q.m_impl.get(), std::function<void()>(task)};
                 int const rc = b200_launch_host_func(q.getNativeHandle(), &trampoline, p);
                 if(rc != 0)
                 {

@@ -139,6 +139,16 @@ namespace alpaka
             {
                 return at(Vec<TDim, TI>{i});
             }
+            template<typename TI>
+            [[nodiscard]] auto at(Vec<TDim, TI> const& idx) const -> TElem const&
+            {
+                return const_cast<ViewOps*>(this)->at(idx);
+            }
+            template<typename TI, typename = std::enable_if_t<std::is_integral_v<TI>>>
+            [[nodiscard]] auto at(TI i) const -> TElem const&
+            {
+                return const_cast<ViewOps*>(this)->at(Vec<TDim, TI>{i});
+            }
             //! contiguous iteration is only meaningful for unpadded views
             [[nodiscard]] auto begin() -> TElem*
             {
@@ -327,9 +337,58 @@ namespace alpaka
         Vec<TDim, TIdx> m_pitches;
     };
 
+    //! Read-only wrapper around another view (held by value): same memory, element type `Elem const`
+    //! (reference: mem/view/ViewConst.hpp:22-60). Wrapping a ViewConst again yields the same type.
+    template<typename TView>
+    class ViewConst : public b200::ViewOps<ViewConst<TView>, std::add_const_t<Elem<TView>>, Dim<TView>, Idx<TView>>
+    {
+        static_assert(!std::is_const_v<TView>, "ViewConst must be instantiated with a non-const view type");
+        static_assert(!std::is_reference_v<TView>, "ViewConst must be instantiated with a non-reference view type");
+
+    public:
+        ViewConst(TView const& view) : m_view(view)
+        {
+        }
+        ViewConst(TView&& view) : m_view(std::move(view))
+        {
+        }
+        [[nodiscard]] auto nativePtr() const -> Elem<TView> const*
+        {
+            return trait::GetPtrNative<TView>::getPtrNative(m_view);
+        }
+        [[nodiscard]] auto extents() const -> Vec<Dim<TView>, Idx<TView>>
+        {
+            return trait::GetExtents<TView>{}(m_view);
+        }
+        [[nodiscard]] auto pitchesInBytes() const -> Vec<Dim<TView>, Idx<TView>>
+        {
+            return trait::GetPitchesInBytes<TView>{}(m_view);
+        }
+        TView m_view;
+    };
+    template<typename TView>
+    ViewConst(TView) -> ViewConst<std::decay_t<TView>>;
+    template<typename TView>
+    ViewConst(ViewConst<TView>) -> ViewConst<std::decay_t<TView>>;
+
     // -----------------------------------------------------------------------------------------------------------
     namespace detail
     {
+        //! byte pitches of a dense (unpadded) row-major array of TElem (reference: mem/view/Traits.hpp:35-49)
+        template<typename TElem, typename TDim, typename TIdx>
+        [[nodiscard]] ALPAKA_FN_HOST_ACC constexpr auto calculatePitchesFromExtents(Vec<TDim, TIdx> const& extent)
+            -> Vec<TDim, TIdx>
+        {
+            Vec<TDim, TIdx> p{};
+            TIdx stride = static_cast<TIdx>(sizeof(TElem));
+            for(std::size_t d = TDim::value; d-- > 0u;)
+            {
+                p[d] = stride;
+                stride = static_cast<TIdx>(stride * extent[d]);
+            }
+            return p;
+        }
+
         template<typename T>
         inline constexpr bool isB200View = false;
         template<typename E, typename D, typename I>
@@ -340,6 +399,8 @@ namespace alpaka
         inline constexpr bool isB200View<ViewPlainPtr<V, E, D, I>> = true;
         template<typename V, typename E, typename D, typename I>
         inline constexpr bool isB200View<ViewSubView<V, E, D, I>> = true;
+        template<typename V>
+        inline constexpr bool isB200View<ViewConst<V>> = true;
     } // namespace detail
 
     namespace concepts
@@ -438,6 +499,66 @@ namespace alpaka
             D,
             I)
 #undef ALPAKA_B200_VIEW_TRAITS
+
+        template<typename V>
+        struct DevType<ViewConst<V>> : DevType<V>
+        {
+        };
+        template<typename V>
+        struct DimType<ViewConst<V>> : DimType<V>
+        {
+        };
+        template<typename V>
+        struct IdxType<ViewConst<V>> : IdxType<V>
+        {
+        };
+        template<typename V>
+        struct ElemType<ViewConst<V>>
+        {
+            using type = std::add_const_t<typename ElemType<V>::type>;
+        };
+        template<typename V>
+        struct GetDev<ViewConst<V>>
+        {
+            static auto getDev(ViewConst<V> const& v)
+            {
+                return alpaka::getDev(v.m_view);
+            }
+        };
+        template<typename V>
+        struct GetExtents<ViewConst<V>>
+        {
+            auto operator()(ViewConst<V> const& v) const
+            {
+                return v.extents();
+            }
+        };
+        template<typename V>
+        struct GetOffsets<ViewConst<V>>
+        {
+            auto operator()(ViewConst<V> const& v) const
+            {
+                return alpaka::getOffsets(v.m_view);
+            }
+        };
+        //! there is no mutable access through a ViewConst
+        template<typename V>
+        struct GetPtrNative<ViewConst<V>>
+        {
+            using E = typename ElemType<V>::type;
+            static auto getPtrNative(ViewConst<V> const& v) -> E const*
+            {
+                return v.nativePtr();
+            }
+        };
+        template<typename V>
+        struct GetPitchesInBytes<ViewConst<V>>
+        {
+            auto operator()(ViewConst<V> const& v) const
+            {
+                return v.pitchesInBytes();
+            }
+        };
 
         // ---- std::vector and std::array are 1-D host views (reference: mem/view/ViewStdVector.hpp, ViewStdArray.hpp)
         template<typename TElem, typename TAlloc>
@@ -1093,15 +1214,18 @@ namespace alpaka
         {
             static void enqueue(QueueCpu<TProperty>& q, b200::TaskCopy<TDim> const& task)
             {
-                std::lock_guard<std::mutex> l(q.m_impl->m_mutex);
-                if(task.deviceInvolved)
-                {
-                    // a host queue copying from/to device memory: synchronous copy on the legacy stream
-                    task.enqueueOn(nullptr);
-                    b200::check(b200_stream_sync(nullptr));
-                }
-                else
-                    task.runOnHost();
+                q.m_impl->run(
+                    [task]
+                    {
+                        if(task.deviceInvolved)
+                        {
+                            // a host queue copying from/to device memory: synchronous copy on the legacy stream
+                            task.enqueueOn(nullptr);
+                            b200::check(b200_stream_sync(nullptr));
+                        }
+                        else
+                            task.runOnHost();
+                    });
             }
         };
         template<typename TProperty, typename TDim>
@@ -1125,14 +1249,17 @@ namespace alpaka
         {
             static void enqueue(QueueCpu<TProperty>& q, b200::TaskSet<TDim> const& task)
             {
-                std::lock_guard<std::mutex> l(q.m_impl->m_mutex);
-                if(task.onHost)
-                    task.runOnHost();
-                else
-                {
-                    task.enqueueOn(nullptr);
-                    b200::check(b200_stream_sync(nullptr));
-                }
+                q.m_impl->run(
+                    [task]
+                    {
+                        if(task.onHost)
+                            task.runOnHost();
+                        else
+                        {
+                            task.enqueueOn(nullptr);
+                            b200::check(b200_stream_sync(nullptr));
+                        }
+                    });
             }
         };
     } // namespace trait

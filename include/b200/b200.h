@@ -158,6 +158,18 @@ extern "C"
     } b200_func_attributes;
     int b200_func_attributes_get(int dev, void const* func, b200_func_attributes* out);
     int b200_launch(int dev, void const* func, uint32_t const grid[3], uint32_t const block[3], size_t dyn_smem_bytes, b200_stream_t s, void** args);
+    /* Device address of a __device__ / __constant__ variable registered with the shared cudart instance
+     * (replaces ApiCudaRt::getSymbolAddress, core/ApiCudaRt.hpp, as used by the device-global copies in
+     * mem/global/DeviceGlobalUniformCudaHipBuiltIn.hpp:43-200). */
+    int b200_symbol_address(int dev, void const* symbol, void** out);
+
+    /* Stream memory operations: `s` blocks until the 32-bit word at `addr` (device memory or pinned-mapped host
+     * memory, 4-byte aligned) is >= value / writes `value` to it in stream order. Replaces the driver-API
+     * cuStreamWaitValue32 call the reference's test helper makes directly
+     * (include/alpaka/test/event/EventHostManualTrigger.hpp:407-417, 440-468); the driver entry points are resolved at
+     * run time through cudaGetDriverEntryPoint, so libcuda is not a link dependency. B200_ENODEV if unavailable. */
+    int b200_stream_wait_value32(int dev, b200_stream_t s, void* addr, uint32_t value);
+    int b200_stream_write_value32(int dev, b200_stream_t s, void* addr, uint32_t value);
 
     /* ---------------------------------------------------------------------------------------------
      * Work-division selection (host logic, no device needed)

@@ -35,7 +35,7 @@ def manifest():
 def test_reference_test_group_passes_on_b200(name):
     exe = os.path.join(BIN, name)
     assert os.path.exists(exe), f"{exe} missing: build it with `make -C tests/conformance` where /root/reference exists"
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([exe, "--skip-benchmarks"], capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert "All tests passed" in r.stdout, tail
