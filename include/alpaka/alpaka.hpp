@@ -19,6 +19,7 @@
 #include "b200/WorkDiv.hpp"
 #include "b200/Acc.hpp"
 #include "b200/Global.hpp"
+#include "b200/Exec.hpp"
 #include "b200/Kernel.hpp"
 #include "b200/Native.hpp"
 #include "b200/Heat2D.hpp"

@@ -7,7 +7,12 @@
 // the reference's per-back-end ALPAKA_ACC_*_ENABLED matrix collapses to the two macros defined below.
 #pragma once
 
+// standard headers the reference's umbrella header brings in transitively and user code relies on (e.g. std::iota in
+// example/convolution2D/src/convolution2D.cpp:253 with no <numeric> of its own)
+#include <algorithm>
 #include <cassert>
+#include <functional>
+#include <numeric>
 #include <cstddef>
 #include <cstdint>
 #include <cstdio>

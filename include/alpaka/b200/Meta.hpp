@@ -109,7 +109,8 @@ namespace alpaka::meta
     template<typename TList, template<typename...> class TApplicee>
     using Apply = typename detail::ApplyImpl<TList, TApplicee>::type;
 
-    // ---- CartesianProduct<List, Lists...>: List<List<a,b,...>...>, first list varies slowest
+    // ---- CartesianProduct<List, Lists...>: List<List<a,b,...>...>, first list varies FASTEST (the order the reference's
+    //      test/unit/meta/src/CartesianProductTest.cpp:20-29 pins)
     namespace detail
     {
         template<template<typename...> class TList, typename TPrefixes, typename... TLists>
@@ -129,9 +130,9 @@ namespace alpaka::meta
         template<template<typename...> class TList, typename... TPrefixes, typename... Ts, typename... TRest>
         struct CartesianImpl<TList, TList<TPrefixes...>, TList<Ts...>, TRest...>
         {
-            template<typename TPrefix>
-            using Expand = TList<typename Append<TPrefix, Ts>::type...>;
-            using type = typename CartesianImpl<TList, Concatenate<Expand<TPrefixes>...>, TRest...>::type;
+            template<typename T>
+            using Expand = TList<typename Append<TPrefixes, T>::type...>;
+            using type = typename CartesianImpl<TList, Concatenate<Expand<Ts>...>, TRest...>::type;
         };
     } // namespace detail
     template<template<typename...> class TList, typename... TLists>

@@ -1,0 +1,4 @@
+// Compatibility path: the reference splits its API over many headers and user code includes some of them directly
+// (here: <alpaka/dev/DevCpu.hpp>). In this implementation the whole API comes from the umbrella header.
+#pragma once
+#include <alpaka/alpaka.hpp>

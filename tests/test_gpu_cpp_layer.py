@@ -63,6 +63,33 @@ def test_reference_babelstream_driver_unmodified(native):
     assert "AccGpuB200<1,unsigned int>" in r.stdout
 
 
+# Reference examples next to the hot path, compiled unmodified (examples/Makefile REFEX):
+# each is its own checker (exit status + the success line its main() prints).
+REF_EXAMPLES = {
+    "heatEquation": "Execution results correct!",          # 1-D FTCS, example/heatEquation/src/heatEquation.cpp:173-177
+    "vectorAdd": "Execution results correct!",             # example/vectorAdd/src/vectorAdd.cpp:166-180
+    "convolution1D": "All results are correct!",           # example/convolution1D/src/convolution1D.cpp:187
+    "convolution2D": "Sampled result checks are correct!", # example/convolution2D/src/convolution2D.cpp:391
+    "parallelLoopPatterns": "Test passed.",                # five loop patterns, each checked by testResult() (:34-51)
+    "helloWorld": "[z:0, y:0, x:0]",                       # device printf of the first thread
+    "helloWorldLambda": None,
+    "kernelSpecialization": None,
+    "tagSpecialization": None,
+    "openMPSchedule": None,
+    "ls": "AccGpuB200<1,int>",
+}
+
+
+@pytest.mark.parametrize("name", sorted(REF_EXAMPLES))
+def test_reference_example_unmodified(name):
+    r = run("ref_ex_" + name)
+    marker = REF_EXAMPLES[name]
+    out = r.stdout + r.stderr
+    assert "incorrect" not in out.lower() and "Test failed" not in out, out[-2000:]
+    if marker is not None:
+        assert marker in out, out[-2000:]
+
+
 # ---------------------------------------------------------------------------------- BabelStream parity vs the oracle
 @pytest.mark.parametrize("native", [True, False])
 @pytest.mark.parametrize("precision", ["double", "float"])
