@@ -403,6 +403,199 @@ namespace
         }
     }
 
+
+    // ------------------------------------------------------------------------------------------------------------
+    // TWO time levels per launch (temporal blocking). A stand-alone field is HBM-bound at one read + one write per cell
+    // per step (16 B); fusing two steps reads level s and writes level s+2 only, i.e. 8 B per cell per step, below
+    // what the one-step roofline allows. The arithmetic per cell and per level is the reference's, so results stay
+    // bit-identical: level s+1 is never stored, it lives in registers.
+    //   * tile TYT x 128 outputs; its (TYT+4) x 132 input box (halo 2) arrives by ONE TMA copy, zero-filled outside the
+    //     field; one tile per CTA (enough CTAs are resident per SM to hide the copy).
+    //   * a thread owns a column pair (c, c+1) and walks RPT rows. Per output row it loads the next level-s row as
+    //     three 16-byte LDS (columns c-2..c+3), computes level s+1 at the FOUR columns c-1..c+2 of the row below
+    //     (its two neighbours' values are recomputed instead of exchanged: no shared-memory round trip, no barrier),
+    //     then level s+2 at its own pair from the three level-(s+1) rows it keeps in registers.
+    //     FP64 work: (4 (RPT+1) + 2 RPT) / RPT stencils per pair-row = 6.25 at RPT 16 (a one-step kernel needs 2 per
+    //     step), which the FP64 pipe of sm_100 (64 lanes/clk/SM) still hides behind HBM; shared-memory traffic per two
+    //     steps equals the one-step kernel's per ONE step.
+    //   * ring cells of the intermediate level take tf1 * (sx[i] + sy[j]) (BoundaryKernel of step s+1), ring cells of
+    //     the output tf2 * (...); only tiles touching the field edge run the tested path (EDGE), interior tiles carry
+    //     no per-cell tests at all.
+    // Only for stand-alone fields (all four sides physical boundaries): a decomposed tile would need ghost cells two
+    // deep.
+    template<int TYT>
+    struct Step2Geom
+    {
+        static constexpr int kBoxY = TYT + 4;
+        static constexpr int kBoxBytes = BOX_X * kBoxY * 8;
+    };
+
+    struct Heat2Args
+    {
+        double* dst;
+        size_t pitchElems;
+        uint32_t ny, nx;
+        uint32_t tilesX;
+        double k, rX, rY, tf1, tf2;
+        double const* sx;
+        double const* sy;
+    };
+
+    struct Row6
+    {
+        double2 a, b, c; // columns c-2,c-1 | c,c+1 | c+2,c+3
+    };
+
+    __device__ __forceinline__ Row6 ldsRow(double const* q)
+    {
+        return Row6{lds128(q), lds128(q + 2), lds128(q + 4)};
+    }
+
+    // exactSolution on the ring at a given time factor; corners and everything outside the field: 0 (never consumed)
+    __device__ __forceinline__ double ringOrZero(Heat2Args const& A, uint32_t j, uint32_t i, double tf)
+    {
+        bool const iCore = i >= 1 && i <= A.nx;
+        bool const jCore = j >= 1 && j <= A.ny;
+        bool const rowRing = j == 0 || j == A.ny + 1;
+        bool const colRing = i == 0 || i == A.nx + 1;
+        if((rowRing && iCore) || (colRing && jCore))
+            return __dmul_rn(tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
+        return 0.0;
+    }
+
+    // level s+1 at row gj, columns gi-1 .. gi+2, from the level-s rows above (up), at (cur) and below (dn) it
+    template<bool EDGE>
+    __device__ __forceinline__ void level1Row(
+        Heat2Args const& A,
+        Row6 const& up,
+        Row6 const& cur,
+        Row6 const& dn,
+        uint32_t gj,
+        uint32_t gi,
+        double (&o)[4])
+    {
+        o[0] = ftcs(cur.a.y, cur.a.x, cur.b.x, up.a.y, dn.a.y, A.k, A.rX, A.rY);
+        o[1] = ftcs(cur.b.x, cur.a.y, cur.b.y, up.b.x, dn.b.x, A.k, A.rX, A.rY);
+        o[2] = ftcs(cur.b.y, cur.b.x, cur.c.x, up.b.y, dn.b.y, A.k, A.rX, A.rY);
+        o[3] = ftcs(cur.c.x, cur.b.y, cur.c.y, up.c.x, dn.c.x, A.k, A.rX, A.rY);
+        if constexpr(EDGE)
+        {
+            bool const jCore = gj >= 1 && gj <= A.ny; // (uint32 wrap of gj = y0 - 1 at y0 = 0 fails both tests, as it must)
+#pragma unroll
+            for(int q = 0; q < 4; ++q)
+            {
+                uint32_t const i = gi + uint32_t(q) - 1u;
+                if(!(jCore && i >= 1 && i <= A.nx))
+                    o[q] = ringOrZero(A, gj, i, A.tf1);
+            }
+        }
+    }
+
+    template<int HINT, int TYT, int RPT, bool EDGE>
+    __device__ __forceinline__ void step2Rows(Heat2Args const& A, double const* box, uint32_t y0, uint32_t x0, int cp, int r0)
+    {
+        // box(row, col): row = tile row + 2, col = tile column + 2; p points at tile row r0-2, column 2cp-2
+        double const* p = box + size_t(r0) * BOX_X + 2 * cp;
+        uint32_t const gi = x0 + 2u * uint32_t(cp);
+        uint32_t gj = y0 + uint32_t(r0);
+
+        Row6 prev = ldsRow(p); // level s, tile row r0-2
+        Row6 cur = ldsRow(p + BOX_X); //          r0-1
+        Row6 next = ldsRow(p + 2 * BOX_X); //     r0
+        double l1[4];
+        level1Row<EDGE>(A, prev, cur, next, gj - 1u, gi, l1); // level s+1, row r0-1 (only columns c, c+1 are used)
+        double up0 = l1[1], up1 = l1[2];
+        prev = cur;
+        cur = next;
+        next = ldsRow(p + 3 * BOX_X); // r0+1
+        double c1[4];
+        level1Row<EDGE>(A, prev, cur, next, gj, gi, c1); // level s+1, row r0
+        prev = cur;
+        cur = next;
+
+        double* out = A.dst + size_t(gj) * A.pitchElems + gi;
+#pragma unroll
+        for(int r = 0; r < RPT; ++r)
+        {
+            next = ldsRow(p + size_t(r + 4) * BOX_X); // level s, tile row r0+r+2
+            double n1[4];
+            level1Row<EDGE>(A, prev, cur, next, gj + 1u, gi, n1); // level s+1, row r0+r+1
+            double v0 = ftcs(c1[1], c1[0], c1[2], up0, n1[1], A.k, A.rX, A.rY);
+            double v1 = ftcs(c1[2], c1[1], c1[3], up1, n1[2], A.k, A.rX, A.rY);
+            if constexpr(!EDGE)
+            {
+                stg2<HINT>(out, v0, v1);
+            }
+            else
+            {
+                bool const jIn = gj <= A.ny + 1u;
+                bool const jCore = gj >= 1 && gj <= A.ny;
+                bool w0 = false, w1 = false;
+                if(jIn && gi <= A.nx + 1u)
+                {
+                    bool const core = jCore && gi >= 1 && gi <= A.nx;
+                    bool const ring = !core && ((jCore && (gi == 0 || gi == A.nx + 1u)) || (!jCore && gi >= 1 && gi <= A.nx));
+                    if(ring)
+                        v0 = ringOrZero(A, gj, gi, A.tf2);
+                    w0 = core || ring;
+                }
+                if(jIn && gi + 1u <= A.nx + 1u)
+                {
+                    bool const core = jCore && gi + 1u <= A.nx; // gi + 1 >= 1 always
+                    bool const ring = !core && ((jCore && gi + 1u == A.nx + 1u) || (!jCore && gi + 1u <= A.nx));
+                    if(ring)
+                        v1 = ringOrZero(A, gj, gi + 1u, A.tf2);
+                    w1 = core || ring;
+                }
+                if(w0 && w1)
+                    stg2<HINT>(out, v0, v1);
+                else if(w0)
+                    out[0] = v0;
+                else if(w1)
+                    out[1] = v1;
+            }
+            up0 = c1[1];
+            up1 = c1[2];
+#pragma unroll
+            for(int q = 0; q < 4; ++q)
+                c1[q] = n1[q];
+            prev = cur;
+            cur = next;
+            out += A.pitchElems;
+            ++gj;
+        }
+    }
+
+    template<int HINT, int TYT, int RPT>
+    __global__ void __launch_bounds__((TX / 2) * (TYT / RPT)) heatStep2Kernel(const __grid_constant__ CUtensorMap mapSrc, Heat2Args const A)
+    {
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t full;
+        int const tid = threadIdx.x;
+        uint32_t const ty = blockIdx.x / A.tilesX;
+        uint32_t const tx = blockIdx.x - ty * A.tilesX;
+        uint32_t const y0 = ty * TYT, x0 = tx * TX;
+        if(tid == 0)
+        {
+            mbarInit(&full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbarExpectTx(&full, Step2Geom<TYT>::kBoxBytes);
+            tmaLoad2d(smem, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 2, &full);
+        }
+        __syncthreads();
+        mbarWait(&full, 0);
+
+        int const cp = tid % (TX / 2);
+        int const r0 = (tid / (TX / 2)) * RPT;
+        double const* box = reinterpret_cast<double const*>(smem);
+        // every level-(s+1) cell this tile computes, rows y0-1..y0+TYT and columns x0-1..x0+TX, is a core cell
+        bool const interior = y0 >= 2 && y0 + TYT <= A.ny && x0 >= 2 && x0 + TX <= A.nx;
+        if(interior)
+            step2Rows<HINT, TYT, RPT, false>(A, box, y0, x0, cp, r0);
+        else
+            step2Rows<HINT, TYT, RPT, true>(A, box, y0, x0, cp, r0);
+    }
+
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
     // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
     __global__ void __launch_bounds__(256) heatBoundaryKernel(HeatArgs const A)
@@ -474,6 +667,34 @@ namespace
             });
         return fn;
     }
+
+    // TMA descriptor of one padded field: (ny+2) x (nx+2) doubles at `pitchBytes`, box BOX_X x boxY
+    bool encodeFieldMap(EncodeTiledFn enc, CUtensorMap* map, double* base, size_t pitchBytes, uint32_t ny, uint32_t nx, int boxY)
+    {
+        int64_t const promoSel = b200::tune("heat.l2promo", 256);
+        CUtensorMapL2promotion const promo = promoSel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                             : promoSel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                             : promoSel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                               : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+        cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(ny) + 2};
+        cuuint64_t const strides[1] = {cuuint64_t(pitchBytes)};
+        cuuint32_t const box[2] = {cuuint32_t(BOX_X), cuuint32_t(boxY)};
+        cuuint32_t const estr[2] = {1, 1};
+        return enc(
+                   map,
+                   CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
+                   2,
+                   base,
+                   dims,
+                   strides,
+                   box,
+                   estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE,
+                   promo,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+               == CUDA_SUCCESS;
+    }
 } // namespace
 
 struct b200_heat2d_plan_st
@@ -486,6 +707,8 @@ struct b200_heat2d_plan_st
     double* sx;
     double* sy;
     CUtensorMap map[2];
+    CUtensorMap map2[2]; // two-level kernel: box (TYT+4) x 132 at tile height map2Tyt (0 = not built yet)
+    int map2Tyt = 0;
     // fused halo exchange (b200_heat2d_plan_set_halo)
     bool hasHalo = false;
     b200_heat2d_halo halo{};
@@ -525,31 +748,9 @@ extern "C"
         plan->ny = ny;
         plan->nx = nx;
         plan->edges = edges;
-        int64_t const promoSel = b200::tune("heat.l2promo", 256);
-        CUtensorMapL2promotion const promo = promoSel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                                             : promoSel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                             : promoSel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-                                                               : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         for(int b = 0; b < 2; ++b)
         {
-            cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(ny) + 2};
-            cuuint64_t const strides[1] = {cuuint64_t(pitch_bytes)};
-            cuuint32_t const box[2] = {BOX_X, BOX_Y};
-            cuuint32_t const estr[2] = {1, 1};
-            CUresult const r = enc(
-                &plan->map[b],
-                CU_TENSOR_MAP_DATA_TYPE_FLOAT64,
-                2,
-                plan->u[b],
-                dims,
-                strides,
-                box,
-                estr,
-                CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_NONE,
-                promo,
-                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if(r != CUDA_SUCCESS)
+            if(!encodeFieldMap(enc, &plan->map[b], plan->u[b], pitch_bytes, ny, nx, BOX_Y))
             {
                 delete plan;
                 return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
@@ -563,15 +764,20 @@ extern "C"
             e = cudaMemcpy(plan->sx, sx_host, bx, cudaMemcpyHostToDevice);
         if(e == cudaSuccess)
             e = cudaMemcpy(plan->sy, sy_host, by, cudaMemcpyHostToDevice);
-        auto optIn = [&](auto* kernel)
+        auto optIn = [&](auto* kernel, int bytes = kMaxStages * STAGE_BYTES)
         {
             if(e == cudaSuccess)
-                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxStages * STAGE_BYTES);
+                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         };
         optIn(heatStepKernel<0, 8>);
         optIn(heatStepKernel<1, 8>);
         optIn(heatStepKernel<0, 4>);
         optIn(heatStepKernel<1, 4>);
+        optIn(heatStep2Kernel<1, 32, 8>, Step2Geom<32>::kBoxBytes);
+        optIn(heatStep2Kernel<1, 32, 16>, Step2Geom<32>::kBoxBytes);
+        optIn(heatStep2Kernel<1, 32, 32>, Step2Geom<32>::kBoxBytes);
+        optIn(heatStep2Kernel<1, 64, 16>, Step2Geom<64>::kBoxBytes);
+        optIn(heatStep2Kernel<1, 64, 32>, Step2Geom<64>::kBoxBytes);
         if(e != cudaSuccess)
         {
             cudaFree(plan->sx);
@@ -725,6 +931,82 @@ extern "C"
     {
         B200_REQUIRE(plan, B200_EINVAL);
         return b200_heat2d_step_window_f64(plan, s, src_index, rx, ry, time_factor, 0, plan->ny + 2, 0, plan->nx + 2);
+    }
+
+    int b200_heat2d_step2_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        double time_factor_1,
+        double time_factor_2)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1), B200_EINVAL);
+        // ghost sides would need level s+1 of the neighbour: stand-alone fields only
+        B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(plan->dev));
+        int const tyt = int(b200::tune("heat.step2_ty", 64));
+        int const rpt = int(b200::tune("heat.step2_rpt", 16));
+        B200_REQUIRE(tyt == 32 || tyt == 64, B200_EINVAL);
+        if(plan->map2Tyt != tyt)
+        {
+            EncodeTiledFn const enc = encoder();
+            if(!enc)
+                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+            for(int b = 0; b < 2; ++b)
+                if(!encodeFieldMap(enc, &plan->map2[b], plan->u[b], plan->pitchBytes, plan->ny, plan->nx, tyt + 4))
+                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (two-level box)", __FILE__, __LINE__);
+            plan->map2Tyt = tyt;
+        }
+        Heat2Args A{};
+        A.dst = plan->u[1 - src_index];
+        A.pitchElems = plan->pitchBytes / 8;
+        A.ny = plan->ny;
+        A.nx = plan->nx;
+        A.tilesX = (plan->nx + 2 + TX - 1) / TX;
+        A.rX = rx;
+        A.rY = ry;
+        A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
+        A.tf1 = time_factor_1;
+        A.tf2 = time_factor_2;
+        A.sx = plan->sx;
+        A.sy = plan->sy;
+        uint64_t const tilesY = (uint64_t(plan->ny) + 2 + uint64_t(tyt) - 1) / uint64_t(tyt);
+        uint64_t const grid = tilesY * A.tilesX;
+        B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
+        auto const s = reinterpret_cast<cudaStream_t>(stream);
+        // (the opt-in for more than 48 KB of dynamic shared memory was made per device in b200_heat2d_plan_create)
+        auto launch = [&](auto* kernel, int threads, size_t smemBytes) -> cudaError_t
+        {
+            kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map2[src_index], A);
+            return cudaSuccess;
+        };
+        cudaError_t e = cudaErrorInvalidValue;
+        switch(tyt * 100 + rpt)
+        {
+        case 3208:
+            e = launch(heatStep2Kernel<1, 32, 8>, 64 * 4, Step2Geom<32>::kBoxBytes);
+            break;
+        case 3216:
+            e = launch(heatStep2Kernel<1, 32, 16>, 64 * 2, Step2Geom<32>::kBoxBytes);
+            break;
+        case 3232:
+            e = launch(heatStep2Kernel<1, 32, 32>, 64, Step2Geom<32>::kBoxBytes);
+            break;
+        case 6416:
+            e = launch(heatStep2Kernel<1, 64, 16>, 64 * 4, Step2Geom<64>::kBoxBytes);
+            break;
+        case 6432:
+            e = launch(heatStep2Kernel<1, 64, 32>, 64 * 2, Step2Geom<64>::kBoxBytes);
+            break;
+        default:
+            return b200::fail(B200_EINVAL, "heat.step2_ty/heat.step2_rpt: supported 32/8, 32/16, 32/32, 64/16, 64/32", __FILE__, __LINE__);
+        }
+        if(e != cudaSuccess)
+            return b200::cudaFail(e, "heat2d two-level launch setup", __FILE__, __LINE__);
+        B200_LAUNCH_CHECK();
+        return 0;
     }
 
     int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo)

@@ -80,6 +80,34 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
+        //! two fused steps in ONE launch (b200_heat2d_step2_f64): the intermediate time level stays in registers, HBM
+        //! traffic is one read + one write per cell for both steps, the field is bit-identical to two step() calls.
+        //! The roles of the buffers swap ONCE. Stand-alone fields only (all four sides physical boundaries).
+        template<typename TQueue>
+        void step2(TQueue& queue)
+        {
+            constexpr double pi = math::constants::pi;
+            double const tf1 = std::exp(-pi * pi * ((m_step + 1) * m_dt));
+            double const tf2 = std::exp(-pi * pi * ((m_step + 2) * m_dt));
+            check(b200_heat2d_step2_f64(m_plan, queue.getNativeHandle(), m_cur, m_rX, m_rY, tf1, tf2));
+            m_step += 2;
+            m_cur ^= 1;
+            queue.afterEnqueue();
+        }
+
+        //! `n` steps, pairwise fused where possible
+        template<typename TQueue>
+        void steps(TQueue& queue, std::uint32_t n, bool fuse = true)
+        {
+            while(n >= 2 && fuse)
+            {
+                step2(queue);
+                n -= 2;
+            }
+            while(n-- > 0)
+                step(queue);
+        }
+
         //! 0 if the current field is bufA, 1 if it is bufB
         [[nodiscard]] auto currentIndex() const -> int
         {

@@ -298,6 +298,13 @@ extern "C"
     int b200_heat2d_plan_destroy(b200_heat2d_plan_t plan);
     /* One step reading buffer `src_index` (0 = u0, 1 = u1) and writing the other one. */
     int b200_heat2d_step_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor);
+    /* TWO steps in one launch (temporal blocking; new -- the reference launches Stencil + Boundary per step,
+     * heatEquation2D.cpp:141-168): reads level s from buffer `src_index`, writes level s+2 into the OTHER buffer; level
+     * s+1 exists only in registers, its ring cells take time_factor_1 * (sx + sy), the ring of the result
+     * time_factor_2 * (sx + sy). HBM traffic is one read + one write per cell per TWO steps; the arithmetic per cell and
+     * level is unchanged, so the field is bit-identical to two b200_heat2d_step_f64 calls. Stand-alone fields only
+     * (plan `edges` == B200_EDGE_ALL, no halo): a decomposed tile would need ghost cells two deep. */
+    int b200_heat2d_step2_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor_1, double time_factor_2);
     /* Restrict a step to a row/column window of OUTPUT cells [j0,j1) x [i0,i1) in padded coordinates
      * (used to split interior / edge strips for halo overlap). */
     int b200_heat2d_step_window_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1);

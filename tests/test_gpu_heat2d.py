@@ -10,11 +10,11 @@ from oracle_lib import P
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(ab, queue, u0, steps, dx, dy, dt, **kw):
+def _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=True, **kw):
     ny, nx = u0.shape[0] - 2, u0.shape[1] - 2
     h = ab.heat2d.Heat2D(queue, ny, nx, dx, dy, dt, **kw)
     h.upload(u0)
-    h.step(steps)
+    h.step(steps, fuse=fuse)
     out = h.download()
     h.close()
     return out
@@ -31,8 +31,10 @@ def _init(ny, nx, dx, dy):
 SHAPES = [(64, 64), (1, 1), (1, 7), (9, 1), (16, 16), (33, 129), (31, 127), (100, 257), (256, 1024), (515, 1030)]
 
 
+@pytest.mark.parametrize("fuse", [False, True], ids=["one_step_per_launch", "two_steps_per_launch"])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_heat2d_bit_exact_vs_oracle(gpu, shape):
+def test_heat2d_bit_exact_vs_oracle(gpu, shape, fuse):
+    """25 steps: 25 one-step launches, or 12 two-step launches (b200_heat2d_step2_f64) + 1 one-step launch."""
     ab, dev, queue = gpu
     ny, nx = shape
     dx, dy, dt = ol.heat_params(ny, nx)
@@ -40,9 +42,41 @@ def test_heat2d_bit_exact_vs_oracle(gpu, shape):
     assert ab.heat2d.initial_field(ny, nx, dx, dy).tobytes() == u0.tobytes()
     steps = 25
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
-    got = _run_gpu(ab, queue, u0, steps, dx, dy, dt)
+    got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=fuse)
     assert np.max(np.abs(got - want)) <= 1e-12
     assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("tile", [(32, 8), (32, 16), (32, 32), (64, 16), (64, 32)], ids=lambda t: f"ty{t[0]}_rpt{t[1]}")
+def test_heat2d_two_step_kernel_every_tile_shape(gpu, tile):
+    """Every instantiation of the two-level kernel (heat.step2_ty / heat.step2_rpt) on a rough field whose extents leave
+    partial tiles on both axes: bit-exact against the oracle, ring and corners included."""
+    ab, dev, queue = gpu
+    ny, nx = 203, 391
+    dx, dy, dt = ol.heat_params(ny, nx)
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=21).reshape(ny + 2, nx + 2)
+    want = ol.orc_heat_run(u0, 1, 6, dx, dy, dt)
+    ab.runtime.tune_set("heat.step2_ty", tile[0])
+    ab.runtime.tune_set("heat.step2_rpt", tile[1])
+    try:
+        got = _run_gpu(ab, queue, u0, 6, dx, dy, dt, fuse=True)
+    finally:
+        ab.runtime.tune_set("heat.step2_ty", 64)
+        ab.runtime.tune_set("heat.step2_rpt", 16)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_heat2d_two_step_refuses_decomposed_tiles(gpu):
+    """Ghost sides would need the neighbour's intermediate level: the C ABI refuses instead of computing garbage."""
+    ab, dev, queue = gpu
+    import ctypes as C
+
+    ny, nx = 40, 72
+    dx, dy, dt = ol.heat_params(ny, nx)
+    h = ab.heat2d.Heat2D(queue, ny, nx, dx, dy, dt, edges=ab.heat2d.EDGE_TOP | ab.heat2d.EDGE_LEFT)
+    rc = ab._lib.load().b200_heat2d_step2_f64(h.plan, queue.handle, 0, h.rx, h.ry, 1.0, 1.0)
+    assert rc != 0
+    h.close()
 
 
 def test_heat2d_random_field_bit_exact(gpu):
