@@ -430,15 +430,32 @@ namespace
         static constexpr int kBoxBytes = BOX_X * kBoxY * 8;
     };
 
+    // Rows of the array: [0, ny + 2 padY). padY = 1: the reference layout (ring rows 0 and ny+1). padY = 2: a row SLAB of
+    // a field decomposed over several GPUs, ghost rows two deep (rows 0,1 and ny+2,ny+3) because two time levels are
+    // advanced per exchange; on a physical side the inner one (1 / ny+2) is the ring and the outer one is unused.
+    // Columns always carry the reference's one-cell ring (slabs keep the full width).
     struct Heat2Args
     {
         double* dst;
         size_t pitchElems;
         uint32_t ny, nx;
+        uint32_t loY, hiY; // first / last core row = padY, ny + padY - 1
+        uint32_t rows; // ny + 2 padY
         uint32_t tilesX;
         double k, rX, rY, tf1, tf2;
         double const* sx;
         double const* sy;
+        uint32_t ghostTop, ghostBottom; // 1: that side has a neighbour (its rows next to the core are ghost cells)
+        // tile order: strip tile rows first (top: tile row 0; bottom: tile rows tyBot..), then the interior
+        uint32_t nTop, nBot, tyBot;
+        // ---- fused halo exchange of a slab; null / 0 for a stand-alone field
+        double* peerDst[2]; // [top, bottom] neighbour's destination buffer of this launch
+        uint32_t* peerFlag[2];
+        uint32_t* myFlags; // slots [0] top, [1] bottom, set by the neighbours
+        uint32_t* stripCounter;
+        uint32_t* status;
+        uint32_t stripTiles;
+        uint32_t step; // 1-based index of this launch (it produces time level 2 * step)
     };
 
     struct Row6
@@ -451,12 +468,13 @@ namespace
         return Row6{lds128(q), lds128(q + 2), lds128(q + 4)};
     }
 
-    // exactSolution on the ring at a given time factor; corners and everything outside the field: 0 (never consumed)
+    // exactSolution on the ring at a given time factor; corners, ghost cells and everything outside the field: 0
+    // (never consumed)
     __device__ __forceinline__ double ringOrZero(Heat2Args const& A, uint32_t j, uint32_t i, double tf)
     {
         bool const iCore = i >= 1 && i <= A.nx;
-        bool const jCore = j >= 1 && j <= A.ny;
-        bool const rowRing = j == 0 || j == A.ny + 1;
+        bool const jCore = j >= A.loY && j <= A.hiY;
+        bool const rowRing = (j + 1u == A.loY && !A.ghostTop) || (j == A.hiY + 1u && !A.ghostBottom);
         bool const colRing = i == 0 || i == A.nx + 1;
         if((rowRing && iCore) || (colRing && jCore))
             return __dmul_rn(tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
@@ -480,12 +498,14 @@ namespace
         o[3] = ftcs(cur.c.x, cur.b.y, cur.c.y, up.c.x, dn.c.x, A.k, A.rX, A.rY);
         if constexpr(EDGE)
         {
-            bool const jCore = gj >= 1 && gj <= A.ny; // (uint32 wrap of gj = y0 - 1 at y0 = 0 fails both tests, as it must)
+            // the stencil applies on core rows and on the neighbours' rows next to them (ghost rows, two deep, hold
+            // level s); (uint32 wrap of gj = y0 - 1 at y0 = 0 fails the range test, as it must)
+            bool const jStencil = gj + A.ghostTop >= A.loY && gj <= A.hiY + A.ghostBottom;
 #pragma unroll
             for(int q = 0; q < 4; ++q)
             {
                 uint32_t const i = gi + uint32_t(q) - 1u;
-                if(!(jCore && i >= 1 && i <= A.nx))
+                if(!(jStencil && i >= 1 && i <= A.nx))
                     o[q] = ringOrZero(A, gj, i, A.tf1);
             }
         }
@@ -528,21 +548,23 @@ namespace
             }
             else
             {
-                bool const jIn = gj <= A.ny + 1u;
-                bool const jCore = gj >= 1 && gj <= A.ny;
+                bool const jCore = gj >= A.loY && gj <= A.hiY;
+                bool const jRing = (gj + 1u == A.loY && !A.ghostTop) || (gj == A.hiY + 1u && !A.ghostBottom);
                 bool w0 = false, w1 = false;
-                if(jIn && gi <= A.nx + 1u)
+                if(gi <= A.nx + 1u)
                 {
-                    bool const core = jCore && gi >= 1 && gi <= A.nx;
-                    bool const ring = !core && ((jCore && (gi == 0 || gi == A.nx + 1u)) || (!jCore && gi >= 1 && gi <= A.nx));
+                    bool const iCore = gi >= 1 && gi <= A.nx;
+                    bool const core = jCore && iCore;
+                    bool const ring = (jCore && !iCore) || (jRing && iCore);
                     if(ring)
                         v0 = ringOrZero(A, gj, gi, A.tf2);
                     w0 = core || ring;
                 }
-                if(jIn && gi + 1u <= A.nx + 1u)
+                if(gi + 1u <= A.nx + 1u)
                 {
-                    bool const core = jCore && gi + 1u <= A.nx; // gi + 1 >= 1 always
-                    bool const ring = !core && ((jCore && gi + 1u == A.nx + 1u) || (!jCore && gi + 1u <= A.nx));
+                    bool const iCore = gi + 1u <= A.nx; // gi + 1 >= 1 always
+                    bool const core = jCore && iCore;
+                    bool const ring = (jCore && !iCore) || (jRing && iCore);
                     if(ring)
                         v1 = ringOrZero(A, gj, gi + 1u, A.tf2);
                     w1 = core || ring;
@@ -553,6 +575,26 @@ namespace
                     out[0] = v0;
                 else if(w1)
                     out[1] = v1;
+                // fused halo exchange: my first / last two core rows (ring columns included) are the neighbour's ghost
+                // rows; peer stores (NVLink) from the registers holding the fresh values. Slabs have equal heights, so
+                // my row gj is the upper neighbour's row gj + ny and the lower neighbour's row gj - ny.
+                if(jCore && (w0 || w1))
+                {
+                    double* peer = nullptr;
+                    if(A.peerDst[0] != nullptr && gj <= A.loY + 1u)
+                        peer = A.peerDst[0] + size_t(gj + A.ny) * A.pitchElems + gi;
+                    else if(A.peerDst[1] != nullptr && gj + 1u >= A.hiY)
+                        peer = A.peerDst[1] + size_t(gj - A.ny) * A.pitchElems + gi;
+                    if(peer != nullptr)
+                    {
+                        if(w0 && w1)
+                            stg2<0>(peer, v0, v1);
+                        else if(w0)
+                            peer[0] = v0;
+                        else
+                            peer[1] = v1;
+                    }
+                }
             }
             up0 = c1[1];
             up1 = c1[2];
@@ -572,13 +614,41 @@ namespace
         extern __shared__ __align__(128) unsigned char smem[];
         __shared__ uint64_t full;
         int const tid = threadIdx.x;
-        uint32_t const ty = blockIdx.x / A.tilesX;
-        uint32_t const tx = blockIdx.x - ty * A.tilesX;
+        uint32_t const ord = blockIdx.x / A.tilesX; // tile row in launch order: strips first
+        uint32_t const tx = blockIdx.x - ord * A.tilesX;
+        bool const strip = ord < A.nTop + A.nBot;
+        uint32_t const ty = ord < A.nTop ? ord : (strip ? A.tyBot + (ord - A.nTop) : A.nTop + (ord - A.nTop - A.nBot));
         uint32_t const y0 = ty * TYT, x0 = tx * TX;
         if(tid == 0)
         {
             mbarInit(&full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if(strip && A.myFlags != nullptr)
+            {
+                // Strip tiles read ghost rows: they hold the neighbours' border rows of the previous launch's time level
+                // once the neighbours' flags say so (which also means the neighbours are done READING the ghost rows
+                // this launch will overwrite in their other buffer). Bounded spin (about 2 s).
+                for(int side = 0; side < 2; ++side)
+                {
+                    if(A.peerDst[side] == nullptr)
+                        continue;
+                    uint32_t seen = 0, spins = 0;
+                    for(;;)
+                    {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
+                        if(seen + 1u >= A.step)
+                            break;
+                        if(++spins > 2000000u)
+                        {
+                            atomicExch(A.status, 1u + uint32_t(side));
+                            break;
+                        }
+                        __nanosleep(1000);
+                    }
+                }
+                // ghosts were written through the generic proxy (peer stores); TMA reads through the async proxy
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             mbarExpectTx(&full, Step2Geom<TYT>::kBoxBytes);
             tmaLoad2d(smem, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 2, &full);
         }
@@ -588,12 +658,33 @@ namespace
         int const cp = tid % (TX / 2);
         int const r0 = (tid / (TX / 2)) * RPT;
         double const* box = reinterpret_cast<double const*>(smem);
-        // every level-(s+1) cell this tile computes, rows y0-1..y0+TYT and columns x0-1..x0+TX, is a core cell
-        bool const interior = y0 >= 2 && y0 + TYT <= A.ny && x0 >= 2 && x0 + TX <= A.nx;
+        // every level-(s+1) cell this tile computes, rows y0-1..y0+TYT and columns x0-1..x0+TX, is a core cell, and no
+        // row of the tile travels to a neighbour
+        bool const interior = !strip && y0 >= A.loY + 1u && y0 + TYT <= A.hiY && x0 >= 2 && x0 + TX <= A.nx;
         if(interior)
             step2Rows<HINT, TYT, RPT, false>(A, box, y0, x0, cp, r0);
         else
             step2Rows<HINT, TYT, RPT, true>(A, box, y0, x0, cp, r0);
+
+        if(strip && A.stripCounter != nullptr)
+        {
+            // every thread has issued this strip tile's (peer) stores: count the tile; whoever finishes the LAST strip tile
+            // of the launch publishes the launch index to the neighbours
+            __syncthreads();
+            if(tid == 0)
+            {
+                __threadfence_system();
+                uint32_t const done = atomicAdd(A.stripCounter, 1u);
+                if(done == A.stripTiles - 1u)
+                {
+                    __threadfence_system();
+                    *A.stripCounter = 0u;
+                    for(int side = 0; side < 2; ++side)
+                        if(A.peerFlag[side] != nullptr)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
+                }
+            }
+        }
     }
 
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
@@ -668,15 +759,15 @@ namespace
         return fn;
     }
 
-    // TMA descriptor of one padded field: (ny+2) x (nx+2) doubles at `pitchBytes`, box BOX_X x boxY
-    bool encodeFieldMap(EncodeTiledFn enc, CUtensorMap* map, double* base, size_t pitchBytes, uint32_t ny, uint32_t nx, int boxY)
+    // TMA descriptor of one padded field: rows x (nx+2) doubles at `pitchBytes`, box BOX_X x boxY
+    bool encodeFieldMap(EncodeTiledFn enc, CUtensorMap* map, double* base, size_t pitchBytes, uint64_t rows, uint32_t nx, int boxY)
     {
         int64_t const promoSel = b200::tune("heat.l2promo", 256);
         CUtensorMapL2promotion const promo = promoSel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                                              : promoSel == 64  ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                                              : promoSel == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
-        cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(ny) + 2};
+        cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(rows)};
         cuuint64_t const strides[1] = {cuuint64_t(pitchBytes)};
         cuuint32_t const box[2] = {cuuint32_t(BOX_X), cuuint32_t(boxY)};
         cuuint32_t const estr[2] = {1, 1};
@@ -709,6 +800,7 @@ struct b200_heat2d_plan_st
     CUtensorMap map[2];
     CUtensorMap map2[2]; // two-level kernel: box (TYT+4) x 132 at tile height map2Tyt (0 = not built yet)
     int map2Tyt = 0;
+    uint32_t padY = 1; // 1: reference layout (ny+2 rows); 2: row slab with ghost rows two deep (ny+4 rows)
     // fused halo exchange (b200_heat2d_plan_set_halo)
     bool hasHalo = false;
     b200_heat2d_halo halo{};
@@ -717,6 +809,84 @@ struct b200_heat2d_plan_st
 
 extern "C"
 {
+    namespace
+    {
+        int createPlan(
+            int dev,
+            double* u0,
+            double* u1,
+            size_t pitch_bytes,
+            uint32_t ny,
+            uint32_t nx,
+            double const* sx_host,
+            double const* sy_host,
+            int edges,
+            uint32_t padY,
+            b200_heat2d_plan_t* out)
+        {
+            B200_REQUIRE(out && u0 && u1 && sx_host && sy_host, B200_EINVAL);
+            B200_REQUIRE(ny >= 1 && nx >= 1 && (edges & ~B200_EDGE_ALL) == 0, B200_EINVAL);
+            B200_REQUIRE(pitch_bytes >= (size_t(nx) + 2) * 8, B200_EINVAL);
+            B200_REQUIRE(pitch_bytes % 16 == 0, B200_EALIGN);
+            B200_REQUIRE(reinterpret_cast<uintptr_t>(u0) % 16 == 0 && reinterpret_cast<uintptr_t>(u1) % 16 == 0, B200_EALIGN);
+            B200_REQUIRE(uint64_t(ny) + 4 + 64 < 0x7fffffffull && uint64_t(nx) + 2 + TX < 0x7fffffffull, B200_ERANGE);
+            B200_CUDA(cudaSetDevice(dev));
+            EncodeTiledFn const enc = encoder();
+            if(!enc)
+                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+
+            auto* plan = new b200_heat2d_plan_st{};
+            plan->dev = dev;
+            plan->u[0] = u0;
+            plan->u[1] = u1;
+            plan->pitchBytes = pitch_bytes;
+            plan->ny = ny;
+            plan->nx = nx;
+            plan->edges = edges;
+            plan->padY = padY;
+            uint64_t const rows = uint64_t(ny) + 2 * padY;
+            for(int b = 0; b < 2; ++b)
+            {
+                if(!encodeFieldMap(enc, &plan->map[b], plan->u[b], pitch_bytes, rows, nx, BOX_Y))
+                {
+                    delete plan;
+                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
+                }
+            }
+            size_t const bx = (size_t(nx) + 2) * 8, by = size_t(rows) * 8;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&plan->sx), bx);
+            if(e == cudaSuccess)
+                e = cudaMalloc(reinterpret_cast<void**>(&plan->sy), by);
+            if(e == cudaSuccess)
+                e = cudaMemcpy(plan->sx, sx_host, bx, cudaMemcpyHostToDevice);
+            if(e == cudaSuccess)
+                e = cudaMemcpy(plan->sy, sy_host, by, cudaMemcpyHostToDevice);
+            auto optIn = [&](auto* kernel, int bytes = kMaxStages * STAGE_BYTES)
+            {
+                if(e == cudaSuccess)
+                    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+            };
+            optIn(heatStepKernel<0, 8>);
+            optIn(heatStepKernel<1, 8>);
+            optIn(heatStepKernel<0, 4>);
+            optIn(heatStepKernel<1, 4>);
+            optIn(heatStep2Kernel<1, 32, 8>, Step2Geom<32>::kBoxBytes);
+            optIn(heatStep2Kernel<1, 32, 16>, Step2Geom<32>::kBoxBytes);
+            optIn(heatStep2Kernel<1, 32, 32>, Step2Geom<32>::kBoxBytes);
+            optIn(heatStep2Kernel<1, 64, 16>, Step2Geom<64>::kBoxBytes);
+            optIn(heatStep2Kernel<1, 64, 32>, Step2Geom<64>::kBoxBytes);
+            if(e != cudaSuccess)
+            {
+                cudaFree(plan->sx);
+                cudaFree(plan->sy);
+                delete plan;
+                return b200::cudaFail(e, "heat2d plan setup", __FILE__, __LINE__);
+            }
+            *out = plan;
+            return 0;
+        }
+    } // namespace
+
     int b200_heat2d_plan_create(
         int dev,
         double* u0,
@@ -729,64 +899,24 @@ extern "C"
         int edges,
         b200_heat2d_plan_t* out)
     {
-        B200_REQUIRE(out && u0 && u1 && sx_host && sy_host, B200_EINVAL);
-        B200_REQUIRE(ny >= 1 && nx >= 1 && (edges & ~B200_EDGE_ALL) == 0, B200_EINVAL);
-        B200_REQUIRE(pitch_bytes >= (size_t(nx) + 2) * 8, B200_EINVAL);
-        B200_REQUIRE(pitch_bytes % 16 == 0, B200_EALIGN);
-        B200_REQUIRE(reinterpret_cast<uintptr_t>(u0) % 16 == 0 && reinterpret_cast<uintptr_t>(u1) % 16 == 0, B200_EALIGN);
-        B200_REQUIRE(uint64_t(ny) + 2 + TY < 0x7fffffffull && uint64_t(nx) + 2 + TX < 0x7fffffffull, B200_ERANGE);
-        B200_CUDA(cudaSetDevice(dev));
-        EncodeTiledFn const enc = encoder();
-        if(!enc)
-            return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+        return createPlan(dev, u0, u1, pitch_bytes, ny, nx, sx_host, sy_host, edges, 1, out);
+    }
 
-        auto* plan = new b200_heat2d_plan_st{};
-        plan->dev = dev;
-        plan->u[0] = u0;
-        plan->u[1] = u1;
-        plan->pitchBytes = pitch_bytes;
-        plan->ny = ny;
-        plan->nx = nx;
-        plan->edges = edges;
-        for(int b = 0; b < 2; ++b)
-        {
-            if(!encodeFieldMap(enc, &plan->map[b], plan->u[b], pitch_bytes, ny, nx, BOX_Y))
-            {
-                delete plan;
-                return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
-            }
-        }
-        size_t const bx = (size_t(nx) + 2) * 8, by = (size_t(ny) + 2) * 8;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&plan->sx), bx);
-        if(e == cudaSuccess)
-            e = cudaMalloc(reinterpret_cast<void**>(&plan->sy), by);
-        if(e == cudaSuccess)
-            e = cudaMemcpy(plan->sx, sx_host, bx, cudaMemcpyHostToDevice);
-        if(e == cudaSuccess)
-            e = cudaMemcpy(plan->sy, sy_host, by, cudaMemcpyHostToDevice);
-        auto optIn = [&](auto* kernel, int bytes = kMaxStages * STAGE_BYTES)
-        {
-            if(e == cudaSuccess)
-                e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-        };
-        optIn(heatStepKernel<0, 8>);
-        optIn(heatStepKernel<1, 8>);
-        optIn(heatStepKernel<0, 4>);
-        optIn(heatStepKernel<1, 4>);
-        optIn(heatStep2Kernel<1, 32, 8>, Step2Geom<32>::kBoxBytes);
-        optIn(heatStep2Kernel<1, 32, 16>, Step2Geom<32>::kBoxBytes);
-        optIn(heatStep2Kernel<1, 32, 32>, Step2Geom<32>::kBoxBytes);
-        optIn(heatStep2Kernel<1, 64, 16>, Step2Geom<64>::kBoxBytes);
-        optIn(heatStep2Kernel<1, 64, 32>, Step2Geom<64>::kBoxBytes);
-        if(e != cudaSuccess)
-        {
-            cudaFree(plan->sx);
-            cudaFree(plan->sy);
-            delete plan;
-            return b200::cudaFail(e, "heat2d plan setup", __FILE__, __LINE__);
-        }
-        *out = plan;
-        return 0;
+    int b200_heat2d_slab_plan_create(
+        int dev,
+        double* u0,
+        double* u1,
+        size_t pitch_bytes,
+        uint32_t ny,
+        uint32_t nx,
+        double const* sx_host,
+        double const* sy_host,
+        int edges,
+        b200_heat2d_plan_t* out)
+    {
+        // a slab keeps the full width: left and right are physical boundaries; two border rows per side must be distinct
+        B200_REQUIRE((edges & B200_EDGE_LEFT) && (edges & B200_EDGE_RIGHT) && ny >= 4, B200_EINVAL);
+        return createPlan(dev, u0, u1, pitch_bytes, ny, nx, sx_host, sy_host, edges, 2, out);
     }
 
     int b200_heat2d_plan_destroy(b200_heat2d_plan_t plan)
@@ -900,7 +1030,7 @@ extern "C"
         uint32_t i0,
         uint32_t i1)
     {
-        B200_REQUIRE(plan && (src_index == 0 || src_index == 1), B200_EINVAL);
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && plan->padY == 1, B200_EINVAL);
         B200_REQUIRE(j1 <= plan->ny + 2 && i1 <= plan->nx + 2, B200_EINVAL);
         B200_CUDA(cudaSetDevice(plan->dev));
         HeatArgs A = baseArgs(plan, src_index, rx, ry, time_factor);
@@ -910,7 +1040,7 @@ extern "C"
 
     int b200_heat2d_boundary_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int dst_index, double time_factor)
     {
-        B200_REQUIRE(plan && (dst_index == 0 || dst_index == 1), B200_EINVAL);
+        B200_REQUIRE(plan && (dst_index == 0 || dst_index == 1) && plan->padY == 1, B200_EINVAL);
         B200_CUDA(cudaSetDevice(plan->dev));
         HeatArgs A{};
         A.dst = plan->u[dst_index];
@@ -933,6 +1063,102 @@ extern "C"
         return b200_heat2d_step_window_f64(plan, s, src_index, rx, ry, time_factor, 0, plan->ny + 2, 0, plan->nx + 2);
     }
 
+    namespace
+    {
+        // `haloStep` = 0: no exchange (stand-alone field); >= 1: the 1-based launch index of a connected slab
+        int launchStep2(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, double rx, double ry, double tf1, double tf2, uint32_t haloStep)
+        {
+            B200_CUDA(cudaSetDevice(plan->dev));
+            int const tyt = int(b200::tune("heat.step2_ty", 64));
+            int const rpt = int(b200::tune("heat.step2_rpt", 16));
+            B200_REQUIRE(tyt == 32 || tyt == 64, B200_EINVAL);
+            uint32_t const rows = plan->ny + 2 * plan->padY;
+            if(plan->map2Tyt != tyt)
+            {
+                EncodeTiledFn const enc = encoder();
+                if(!enc)
+                    return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+                for(int b = 0; b < 2; ++b)
+                    if(!encodeFieldMap(enc, &plan->map2[b], plan->u[b], plan->pitchBytes, rows, plan->nx, tyt + 4))
+                        return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (two-level box)", __FILE__, __LINE__);
+                plan->map2Tyt = tyt;
+            }
+            Heat2Args A{};
+            A.dst = plan->u[1 - src_index];
+            A.pitchElems = plan->pitchBytes / 8;
+            A.ny = plan->ny;
+            A.nx = plan->nx;
+            A.loY = plan->padY;
+            A.hiY = plan->ny + plan->padY - 1;
+            A.rows = rows;
+            A.tilesX = (plan->nx + 2 + TX - 1) / TX;
+            A.rX = rx;
+            A.rY = ry;
+            A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
+            A.tf1 = tf1;
+            A.tf2 = tf2;
+            A.sx = plan->sx;
+            A.sy = plan->sy;
+            A.ghostTop = (plan->edges & B200_EDGE_TOP) ? 0u : 1u;
+            A.ghostBottom = (plan->edges & B200_EDGE_BOTTOM) ? 0u : 1u;
+            uint32_t const tilesY = (rows + uint32_t(tyt) - 1) / uint32_t(tyt);
+            // strip tile rows: the one holding ghost rows 0,1 and border rows 2,3; the ones holding rows hiY-1.. (border and
+            // ghost rows at the bottom). They come first in the launch so their rows travel while the interior is computed.
+            A.nTop = A.ghostTop ? 1u : 0u;
+            A.tyBot = A.ghostBottom ? (A.hiY - 1u) / uint32_t(tyt) : tilesY;
+            if(A.tyBot < A.nTop)
+                A.tyBot = A.nTop;
+            A.nBot = tilesY - A.tyBot;
+            if(haloStep != 0)
+            {
+                int const dstIndex = 1 - src_index;
+                for(int side = 0; side < 2; ++side)
+                {
+                    A.peerDst[side] = plan->halo.peer_u[side][dstIndex];
+                    A.peerFlag[side] = plan->halo.peer_flag[side];
+                }
+                A.myFlags = plan->halo.my_flags;
+                A.stripCounter = plan->haloScratch;
+                A.status = plan->haloScratch + 1;
+                A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
+                A.step = haloStep;
+                // heat.halo_debug (measurement only, results become wrong): 1 = no peer stores, 2 = no flag wait
+                int64_t const dbg = b200::tune("heat.halo_debug", 0);
+                if(dbg & 1)
+                    A.peerDst[0] = A.peerDst[1] = nullptr;
+                if(dbg & 2)
+                    A.myFlags = nullptr;
+            }
+            uint64_t const grid = uint64_t(tilesY) * A.tilesX;
+            B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
+            auto const s = reinterpret_cast<cudaStream_t>(stream);
+            // (the opt-in for more than 48 KB of dynamic shared memory was made per device when the plan was created)
+            auto launch = [&](auto* kernel, int threads, size_t smemBytes) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map2[src_index], A); };
+            switch(tyt * 100 + rpt)
+            {
+            case 3208:
+                launch(heatStep2Kernel<1, 32, 8>, 64 * 4, Step2Geom<32>::kBoxBytes);
+                break;
+            case 3216:
+                launch(heatStep2Kernel<1, 32, 16>, 64 * 2, Step2Geom<32>::kBoxBytes);
+                break;
+            case 3232:
+                launch(heatStep2Kernel<1, 32, 32>, 64, Step2Geom<32>::kBoxBytes);
+                break;
+            case 6416:
+                launch(heatStep2Kernel<1, 64, 16>, 64 * 4, Step2Geom<64>::kBoxBytes);
+                break;
+            case 6432:
+                launch(heatStep2Kernel<1, 64, 32>, 64 * 2, Step2Geom<64>::kBoxBytes);
+                break;
+            default:
+                return b200::fail(B200_EINVAL, "heat.step2_ty/heat.step2_rpt: supported 32/8, 32/16, 32/32, 64/16, 64/32", __FILE__, __LINE__);
+            }
+            B200_LAUNCH_CHECK();
+            return 0;
+        }
+    } // namespace
+
     int b200_heat2d_step2_f64(
         b200_heat2d_plan_t plan,
         b200_stream_t stream,
@@ -943,70 +1169,24 @@ extern "C"
         double time_factor_2)
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1), B200_EINVAL);
-        // ghost sides would need level s+1 of the neighbour: stand-alone fields only
-        B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo, B200_EINVAL);
-        B200_CUDA(cudaSetDevice(plan->dev));
-        int const tyt = int(b200::tune("heat.step2_ty", 64));
-        int const rpt = int(b200::tune("heat.step2_rpt", 16));
-        B200_REQUIRE(tyt == 32 || tyt == 64, B200_EINVAL);
-        if(plan->map2Tyt != tyt)
-        {
-            EncodeTiledFn const enc = encoder();
-            if(!enc)
-                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
-            for(int b = 0; b < 2; ++b)
-                if(!encodeFieldMap(enc, &plan->map2[b], plan->u[b], plan->pitchBytes, plan->ny, plan->nx, tyt + 4))
-                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (two-level box)", __FILE__, __LINE__);
-            plan->map2Tyt = tyt;
-        }
-        Heat2Args A{};
-        A.dst = plan->u[1 - src_index];
-        A.pitchElems = plan->pitchBytes / 8;
-        A.ny = plan->ny;
-        A.nx = plan->nx;
-        A.tilesX = (plan->nx + 2 + TX - 1) / TX;
-        A.rX = rx;
-        A.rY = ry;
-        A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
-        A.tf1 = time_factor_1;
-        A.tf2 = time_factor_2;
-        A.sx = plan->sx;
-        A.sy = plan->sy;
-        uint64_t const tilesY = (uint64_t(plan->ny) + 2 + uint64_t(tyt) - 1) / uint64_t(tyt);
-        uint64_t const grid = tilesY * A.tilesX;
-        B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
-        auto const s = reinterpret_cast<cudaStream_t>(stream);
-        // (the opt-in for more than 48 KB of dynamic shared memory was made per device in b200_heat2d_plan_create)
-        auto launch = [&](auto* kernel, int threads, size_t smemBytes) -> cudaError_t
-        {
-            kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->map2[src_index], A);
-            return cudaSuccess;
-        };
-        cudaError_t e = cudaErrorInvalidValue;
-        switch(tyt * 100 + rpt)
-        {
-        case 3208:
-            e = launch(heatStep2Kernel<1, 32, 8>, 64 * 4, Step2Geom<32>::kBoxBytes);
-            break;
-        case 3216:
-            e = launch(heatStep2Kernel<1, 32, 16>, 64 * 2, Step2Geom<32>::kBoxBytes);
-            break;
-        case 3232:
-            e = launch(heatStep2Kernel<1, 32, 32>, 64, Step2Geom<32>::kBoxBytes);
-            break;
-        case 6416:
-            e = launch(heatStep2Kernel<1, 64, 16>, 64 * 4, Step2Geom<64>::kBoxBytes);
-            break;
-        case 6432:
-            e = launch(heatStep2Kernel<1, 64, 32>, 64 * 2, Step2Geom<64>::kBoxBytes);
-            break;
-        default:
-            return b200::fail(B200_EINVAL, "heat.step2_ty/heat.step2_rpt: supported 32/8, 32/16, 32/32, 64/16, 64/32", __FILE__, __LINE__);
-        }
-        if(e != cudaSuccess)
-            return b200::cudaFail(e, "heat2d two-level launch setup", __FILE__, __LINE__);
-        B200_LAUNCH_CHECK();
-        return 0;
+        // ghost sides need the neighbour's intermediate level: stand-alone fields only (slabs: b200_heat2d_step2_halo_f64)
+        B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo && plan->padY == 1, B200_EINVAL);
+        return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, 0);
+    }
+
+    int b200_heat2d_step2_halo_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        double time_factor_1,
+        double time_factor_2,
+        uint32_t step)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && step >= 1, B200_EINVAL);
+        B200_REQUIRE(plan->hasHalo && plan->padY == 2, B200_EINVAL);
+        return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, step);
     }
 
     int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo)
@@ -1034,7 +1214,7 @@ extern "C"
 
     int b200_heat2d_step_halo_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, double rx, double ry, double time_factor, uint32_t step)
     {
-        B200_REQUIRE(plan && plan->hasHalo && (src_index == 0 || src_index == 1) && step >= 1, B200_EINVAL);
+        B200_REQUIRE(plan && plan->hasHalo && (src_index == 0 || src_index == 1) && step >= 1 && plan->padY == 1, B200_EINVAL);
         B200_CUDA(cudaSetDevice(plan->dev));
         HeatArgs A = baseArgs(plan, src_index, rx, ry, time_factor);
         uint32_t const H = plan->ny + 2, Wd = plan->nx + 2;

@@ -121,6 +121,134 @@ class HeatTile:
         self.flags.free()
 
 
+class _SlabInfo:
+    """What connect_over_process_group / connect_in_process need to know about a slab (the Tile fields they use)."""
+
+    def __init__(self, rank: int, world: int, ny: int, nx: int):
+        self.rank, self.world, self.ny, self.nx = rank, world, ny, nx
+        self.neighbours = {"top": None if rank == 0 else rank - 1, "bottom": None if rank == world - 1 else rank + 1,
+                           "left": None, "right": None}
+        self.edges = decomp.EDGE_LEFT | decomp.EDGE_RIGHT | (decomp.EDGE_TOP if rank == 0 else 0) | (
+            decomp.EDGE_BOTTOM if rank == world - 1 else 0)
+        self.shape = (ny + 4, nx + 2)
+        self.j_offset = rank * ny  # local row j is global padded row j_offset + j - 1
+
+
+class HeatSlab(HeatTile):
+    """One rank's ROW SLAB of the field, advanced TWO time levels per launch and per exchange
+    (b200_heat2d_slab_plan_create / b200_heat2d_step2_halo_f64, include/b200/b200.h): the temporal blocking of the
+    stand-alone two-level kernel carried to several GPUs. Ghost rows are two deep, so the local array is
+    (ny+4) x (nx+2): rows 0,1 / ny+2,ny+3 are ghosts (or ring + unused on a physical side), core rows are 2..ny+1.
+    Same wiring calls as HeatTile (export / open_peer / connect, connect_over_process_group, connect_in_process)."""
+
+    def __init__(self, queue: Queue, rank: int, world: int, NY: int, NX: int, dt: Optional[float] = None):
+        import math
+
+        if NY % world != 0 or NY // world < 4:
+            raise B200Error(-1, f"heat slabs: {NY} core rows do not divide into {world} slabs of at least 4 rows")
+        self.queue, self.dev = queue, queue.dev
+        self.NY, self.NX = NY, NX
+        ny, nx = NY // world, NX
+        self.tile = _SlabInfo(rank, world, ny, nx)
+        self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)
+        self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
+        if heat2d.stability_ratio(self.dx, self.dy, self.dt) > 1.0:
+            raise B200Error(-1, "Stability condition check failed")
+        self.rx, self.ry = self.dt / (self.dx * self.dx), self.dt / (self.dy * self.dy)
+        self.bufs = [Buf(self.dev, np.float64, (ny + 4, nx + 2), queue, ipc=True) for _ in range(2)]
+        self.cur, self.step_index, self.launch_index = 0, 0, 0
+        pi = math.pi
+        self.sx = np.array([math.sin(pi * (i * self.dx)) for i in range(nx + 2)], dtype=np.float64)
+        self.sy = np.array([math.sin(pi * ((self.tile.j_offset + j - 1) * self.dy)) for j in range(ny + 4)], dtype=np.float64)
+        plan = C.c_void_p()
+        lib = _lib.load()
+        check(lib.b200_heat2d_slab_plan_create(self.dev.idx, self.bufs[0].ptr, self.bufs[1].ptr, self.bufs[0].pitch_bytes,
+                                               ny, nx, self.sx.ctypes.data, self.sy.ctypes.data, self.tile.edges, C.byref(plan)))
+        self.plan = plan.value
+        self.flags = Buf(self.dev, np.uint32, 16, ipc=True)
+        check(lib.b200_memset_async(self.dev.idx, self.flags.ptr, 0, 64, queue.handle))
+        queue.wait()
+        self._opened = []
+        self.connected = False
+        self.h = self  # HeatTile's wiring code reads h.bufs / h.plan
+
+    # ---- data
+    def window(self, global_field: np.ndarray) -> np.ndarray:
+        """This slab's (ny+4) x (nx+2) window of a global (NY+2) x (NX+2) padded field; rows outside the field are 0."""
+        ny = self.tile.ny
+        out = np.zeros((ny + 4, self.NX + 2))
+        g0 = self.tile.j_offset - 1  # global row of local row 0
+        lo, hi = max(g0, 0), min(g0 + ny + 4, self.NY + 2)
+        out[lo - g0 : hi - g0, :] = global_field[lo:hi, :]
+        return out
+
+    def initial_field(self) -> np.ndarray:
+        import math
+
+        return math.exp(-math.pi * math.pi * 0.0) * (self.sx[None, :] + self.sy[:, None])
+
+    def upload(self, local_field: np.ndarray) -> None:
+        local_field = np.ascontiguousarray(local_field, dtype=np.float64)
+        if local_field.shape != self.tile.shape:
+            raise B200Error(-1, "heat slab: field must be (ny+4) x (nx+2)")
+        memcpy(self.queue, self.bufs[0], local_field)
+        memcpy(self.queue, self.bufs[1], local_field)
+        self.queue.wait()
+        self.cur = 0
+
+    def step(self, n: int = 2) -> None:
+        """n FTCS steps, n even: n/2 launches, each advancing two time levels and exchanging two ghost rows per side."""
+        if n % 2 != 0:
+            raise B200Error(-1, "heat slabs advance two time levels per launch: the number of steps must be even")
+        if not self.connected:
+            raise B200Error(-1, "HeatSlab.step before connect()")
+        lib = _lib.load()
+        for _ in range(n // 2):
+            self.launch_index += 1
+            tf1 = heat2d.time_factor(self.step_index + 1, self.dt)
+            tf2 = heat2d.time_factor(self.step_index + 2, self.dt)
+            check(lib.b200_heat2d_step2_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tf1, tf2, self.launch_index))
+            self.step_index += 2
+            self.cur ^= 1
+        self.queue._after_enqueue()
+
+    def status(self) -> int:
+        s = C.c_uint32(0)
+        check(_lib.load().b200_heat2d_halo_status(self.plan, C.byref(s)))
+        return int(s.value)
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.tile.shape, dtype=np.float64)
+        self.queue.wait()
+        memcpy(self.queue, out, self.bufs[self.cur])
+        self.queue.wait()
+        return out
+
+    def stitch(self, global_out: np.ndarray, local_field: np.ndarray) -> None:
+        """Writes the rows this slab OWNS (core rows, plus the physical ring row on a boundary side) into the global
+        (NY+2) x (NX+2) field."""
+        ny, g0 = self.tile.ny, self.tile.j_offset - 1
+        j0 = 1 if self.tile.edges & decomp.EDGE_TOP else 2
+        j1 = ny + 3 if self.tile.edges & decomp.EDGE_BOTTOM else ny + 2
+        global_out[g0 + j0 : g0 + j1, :] = local_field[j0:j1, :]
+
+    def close(self) -> None:
+        lib = _lib.load()
+        for p in self._opened:
+            lib.b200_ipc_close_mem_handle(self.dev.idx, p)
+        self._opened = []
+        if getattr(self, "plan", None):
+            lib.b200_heat2d_plan_destroy(self.plan)
+            self.plan = None
+        for b in self.bufs:
+            b.free()
+        self.bufs = []
+        self.flags.free()
+
+    def __del__(self):
+        pass
+
+
 def connect_over_process_group(tile_runner: HeatTile, dist) -> None:
     """One process per GPU: all-gather the IPC handles (objects, once) and map the neighbours' buffers."""
     world = dist.get_world_size()

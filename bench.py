@@ -377,6 +377,25 @@ def run_ours(args):
             assert err < 1e-4, f"decomposed heat field deviates from the analytic solution: {err}"
             kernels["heat2d_f64"]["max_abs_error_vs_analytic"] = err
             runner.close()
+            # the same field as row slabs advanced TWO time levels per launch and per exchange (ghost rows two deep):
+            # algorithmic bytes stay 16 B per cell per step, half of them are moved
+            slab = multi.HeatSlab(q, rank, world, NY, NX)
+            multi.connect_over_process_group(slab, dist)
+            slab.upload(slab.initial_field())
+            barrier()
+            ms_slab = timed(lambda: slab.step(2), max(50, K), 5)
+            assert slab.status() == 0, "heat slab flag wait timed out"
+            record("heat2d_f64_two_steps_per_launch", ms_slab, 2 * 16.0 * NY * NX / world)
+            kernels["heat2d_f64_two_steps_per_launch"].update(
+                scaling="strong", ms_per_step=round(ms_slab / 2, 4),
+                decomposition=f"{world} row slabs of {NY // world}x{NX}, ghost rows two deep, fused P2P halo")
+            local = slab.download()
+            tmax = slab.step_index * slab.dt
+            exact = math.exp(-math.pi * math.pi * tmax) * (slab.sx[None, :] + slab.sy[:, None])
+            err = float(np.max(np.abs(local[2:-2, 1:-1] - exact[2:-2, 1:-1])))
+            assert err < 1e-4, f"slab-decomposed heat field deviates from the analytic solution: {err}"
+            kernels["heat2d_f64_two_steps_per_launch"]["max_abs_error_vs_analytic"] = err
+            slab.close()
             if not args.heat:
                 # BASELINE.json configs[4]: 65536^2 weak-scaled over 8 GPUs = 16384 x 32768 core cells per GPU; the same
                 # per-GPU tile at other N (halo/interior overlap stress: 2 x 4.3 GB of state per GPU)
@@ -393,6 +412,17 @@ def run_ours(args):
                 kernels["heat2d_f64_weak"]["scaling"] = "weak"
                 kernels["heat2d_f64_weak"]["decomposition"] = f"{NYw}x{NXw} global, {py}x{px} tiles of {tile_w.ny}x{tile_w.nx}"
                 rw.close()
+                sw = multi.HeatSlab(q, rank, world, NYw, NXw)
+                multi.connect_over_process_group(sw, dist)
+                sw.upload(sw.initial_field())
+                barrier()
+                ms_sw = timed(lambda: sw.step(2), max(20, K), 5)
+                assert sw.status() == 0, "heat slab flag wait timed out"
+                record("heat2d_f64_weak_two_steps_per_launch", ms_sw, 2 * 16.0 * NYw * NXw / world)
+                kernels["heat2d_f64_weak_two_steps_per_launch"].update(
+                    scaling="weak", ms_per_step=round(ms_sw / 2, 4),
+                    decomposition=f"{NYw}x{NXw} global, {world} row slabs of {NYw // world}x{NXw}, ghost rows two deep")
+                sw.close()
         q.wait()
 
     # ---- e2e: Triad through the public host API, pinned HOST buffers, copies inside the timed region

@@ -9,6 +9,8 @@
 //                     (native TMA stencil + ring kernel when the functors are recognised, generic trampoline with
 //                     ALPAKA_B200_NATIVE=0)
 //   --mode=fused      per step: one launch of the fused native kernel (alpaka::b200::Heat2DStepper)
+//   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
+//                     (Heat2DStepper::steps -> b200_heat2d_step2_f64; an odd last step runs alone); same bits
 //   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
 //   --output=<file>   dump the final (ny+2) x (nx+2) field, unpadded, for the parity tests
 #include "../common/cli.hpp"
@@ -134,6 +136,15 @@ auto main(int argc, char** argv) -> int
                 stepper.step(computeQueue);
                 ++launches;
             }
+            alpaka::wait(computeQueue);
+            if(stepper.currentIndex() == 1)
+                std::swap(uNextBufAcc, uCurrBufAcc);
+        }
+        else if(mode == "fused2")
+        {
+            alpaka::b200::Heat2DStepper stepper(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
+            stepper.steps(computeQueue, numTimeSteps);
+            launches = numTimeSteps / 2 + numTimeSteps % 2;
             alpaka::wait(computeQueue);
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);

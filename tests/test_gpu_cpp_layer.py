@@ -189,13 +189,15 @@ def test_reduce_f32_exactly_representable_sums(tmp_path):
 
 
 # ---------------------------------------------------------------------------------- heatEquation2D
-@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("functors", True, True), ("functors", False, False)])
+@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("fused2", True, True), ("functors", True, True),
+                                               ("functors", False, False)])
 @pytest.mark.parametrize("shape", [(64, 64), (96, 160)])
 def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
-    """fused and recognised-functor paths: bit-exact (boundary factors from the host libm). Generic trampoline: the
-    reference's BoundaryKernel calls the DEVICE exp/sin, so only the 1e-12 max-abs bar applies."""
+    """fused (one and two steps per launch) and recognised-functor paths: bit-exact (boundary factors from the host
+    libm). Generic trampoline: the reference's BoundaryKernel calls the DEVICE exp/sin, so only the 1e-12 max-abs bar
+    applies. 61 steps: the two-step mode ends with a single-step launch."""
     ny, nx = shape
-    steps = 60
+    steps = 61
     dx, dy, dt = ol.heat_params(ny, nx)
     out = tmp_path / "u.bin"
     r = run("heat2d_b200", f"--ny={ny}", f"--nx={nx}", f"--steps={steps}", f"--dt={dt!r}", f"--mode={mode}", f"--output={out}",
@@ -213,7 +215,7 @@ def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
 
 def test_heat2d_reference_configuration_with_run_time_sizes():
     """The shipped configuration (64x64, 4000 steps, tMax 0.1) through the parameterised driver, both modes."""
-    for mode in ("functors", "fused"):
+    for mode in ("functors", "fused", "fused2"):
         r = run("heat2d_b200", "--ny=64", "--nx=64", "--steps=4000", "--dt=2.5e-05", f"--mode={mode}")
         assert "Execution results correct!" in r.stdout
         assert last_json(r.stdout)["max_error"] < 1e-4

@@ -82,3 +82,72 @@ def test_single_tile_halo_launch_equals_plain_step(gpu):
     got = run_decomposed(ab, dev, NY, NX, (1, 1), steps, cap=0)
     want = oracle_run(NY, NX, steps)
     assert got.tobytes() == want.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Row slabs advanced TWO time levels per launch and per exchange (b200_heat2d_step2_halo_f64): ghost rows two deep.
+def run_slabs(ab, dev, NY, NX, world, steps, u0):
+    from alpaka_b200 import multi
+
+    queues = [ab.Queue(dev) for _ in range(world)]
+    runners = [multi.HeatSlab(q, r, world, NY, NX) for r, q in enumerate(queues)]
+    multi.connect_in_process(runners)
+    for r in runners:
+        r.upload(r.window(u0))
+    for _ in range(steps // 2):
+        for r in runners:
+            r.step(2)
+    for q in queues:
+        q.wait()
+    out = np.full((NY + 2, NX + 2), np.nan)
+    for r in runners:
+        assert r.status() == 0, "a flag wait timed out"
+        r.stitch(out, r.download())
+    for r in runners:
+        r.close()
+    return out
+
+
+# (world, rows per slab, NX): slabs smaller than one 64-row tile (everything is a strip), a slab whose last two core
+# rows straddle two tile rows (ny = 127), slabs with interior tile rows and partial tiles in x, a single slab
+SLAB_CASES = [(2, 20, 96), (3, 61, 200), (2, 127, 391), (4, 200, 700), (1, 150, 300), (8, 64, 256)]
+
+
+@pytest.mark.parametrize("case", SLAB_CASES, ids=lambda c: f"{c[0]}slabs_of_{c[1]}x{c[2]}")
+def test_slabs_two_levels_per_launch_equal_undecomposed(gpu, case):
+    ab, dev, _ = gpu
+    world, ny, NX = case
+    NY, steps = ny * world, 12
+    dx, dy, dt = ol.heat_params(NY, NX)
+    u0 = np.empty((NY + 2, NX + 2))
+    ol.oracle().orc_heat2d_init(P(u0), NY, NX, NX + 2, dx, dy)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    got = run_slabs(ab, dev, NY, NX, world, steps, u0)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_slabs_rough_field_bit_exact(gpu):
+    """A rough field exercises every neighbour term across the slab borders (the analytic field is smooth)."""
+    ab, dev, _ = gpu
+    world, ny, NX, steps = 3, 70, 263, 8
+    NY = ny * world
+    dx, dy, dt = ol.heat_params(NY, NX)
+    u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=33).reshape(NY + 2, NX + 2)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    got = run_slabs(ab, dev, NY, NX, world, steps, u0)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_slab_argument_errors(gpu):
+    ab, dev, queue = gpu
+    from alpaka_b200 import multi
+
+    with pytest.raises(ab.B200Error):  # odd number of steps
+        s = multi.HeatSlab(queue, 0, 1, 64, 64)
+        multi.connect_in_process([s])
+        try:
+            s.step(3)
+        finally:
+            s.close()
+    with pytest.raises(ab.B200Error):  # rows do not divide
+        multi.HeatSlab(queue, 0, 3, 64, 64)
