@@ -687,6 +687,197 @@ namespace
         }
     }
 
+
+    // ------------------------------------------------------------------------------------------------------------
+    // S time levels per launch, S >= 3 (deeper temporal blocking). Recomputing the neighbours' columns as the two-level
+    // kernel does costs (S+1) S stencils per pair-row and would make three levels FP64-bound, so here every thread
+    // computes ONLY its own column pair at every level and takes the two horizontal neighbours' values from the adjacent
+    // lanes by warp shuffle. A warp owns a window of 64 columns; what the edge lanes cannot obtain becomes invalid one
+    // column per level, so after S levels the warp stores the inner 64 - 2M columns (M = 2 (S/2): pairs stay aligned)
+    // and neighbouring warps' windows overlap by 2M columns -- 6.7 % redundant work at S = 3.
+    //   * tile = NWY x RPT rows by NWX x (64 - 2M) columns; its (rows + 2S) x (columns + 2M + 4) input box arrives by ONE
+    //     TMA copy (S = 3: 128 columns = 1 KB per row), zero-filled outside the field;
+    //   * a thread walks down its rows once: per input row 3 LDS.128 (own pair + the pairs left and right of it), then one
+    //     pair of stencils per level as soon as three rows of the level below exist; rows roll through registers;
+    //     per level and row two 64-bit shuffles. FP64 work per pair-row at S = 3, RPT 16: 2 x (20 + 18 + 16) / 16 x 64/60 =
+    //     7.2 stencils for THREE steps (the one-step kernel needs 2 per step).
+    //   * ring cells of intermediate level k take tf[k] * (sx + sy); only tiles touching the field edge test per cell.
+    // Stand-alone fields only.
+    constexpr int kMaxLevels = 4;
+
+    template<int S>
+    struct StepNGeom
+    {
+        static constexpr int M = 2 * (S / 2); // columns a warp window loses on each side
+        static constexpr int NWX = 2; // warps side by side
+        static constexpr int WOUT_WARP = 64 - 2 * M;
+        static constexpr int WOUT = NWX * WOUT_WARP; // output columns per tile
+        static constexpr int BOXX = WOUT + 2 * M + 4; // + M each side + 2 each side so that pairs stay 16-byte aligned
+    };
+
+    struct HeatNArgs
+    {
+        double* dst;
+        size_t pitchElems;
+        uint32_t ny, nx;
+        uint32_t tilesX;
+        double k, rX, rY;
+        double tf[kMaxLevels]; // tf[l-1]: time factor of the l-th level of this launch
+        double const* sx;
+        double const* sy;
+    };
+
+    struct RowN
+    {
+        double x, y, l, r; // own pair, left neighbour's .y, right neighbour's .x
+    };
+
+    __device__ __forceinline__ double shflUp1(double v)
+    {
+        return __shfl_up_sync(0xffffffffu, v, 1);
+    }
+
+    __device__ __forceinline__ double shflDown1(double v)
+    {
+        return __shfl_down_sync(0xffffffffu, v, 1);
+    }
+
+    // exactSolution at a ring cell, 0 anywhere else that is not a core cell (never consumed); j, i may be out of range
+    __device__ __forceinline__ double ringOrZeroN(HeatNArgs const& A, int32_t j, int32_t i, double tf)
+    {
+        bool const iCore = i >= 1 && i <= int32_t(A.nx);
+        bool const jCore = j >= 1 && j <= int32_t(A.ny);
+        bool const rowRing = j == 0 || j == int32_t(A.ny) + 1;
+        bool const colRing = i == 0 || i == int32_t(A.nx) + 1;
+        if((rowRing && iCore) || (colRing && jCore))
+            return __dmul_rn(tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
+        return 0.0;
+    }
+
+    template<int S, int RPT, int NWY, bool EDGE>
+    __device__ __forceinline__ void stepNRows(HeatNArgs const& A, double const* box, int32_t y0, int32_t x0, int wx, int wy, int lane)
+    {
+        using G = StepNGeom<S>;
+        int const r0 = wy * RPT;
+        // box(row, col): row = tile row + S, col = global column - (x0 - M - 2)
+        int const bc = 2 + wx * G::WOUT_WARP + 2 * lane; // box column of the own pair
+        int32_t const gi = x0 - G::M + wx * G::WOUT_WARP + 2 * lane; // its global column
+        double const* p = box + size_t(r0) * G::BOXX + (bc - 2);
+        bool const storeLane = lane >= G::M / 2 && lane < 32 - G::M / 2;
+
+        double U[S][2]; // level l: the row two above the newest one (own pair)
+        RowN C[S]; //              the row one above the newest one
+#pragma unroll
+        for(int i = 0; i < RPT + 2 * S; ++i)
+        {
+            // level 0, tile row r0 - S + i
+            double2 const a = lds128(p + size_t(i) * G::BOXX), b = lds128(p + size_t(i) * G::BOXX + 2),
+                          c = lds128(p + size_t(i) * G::BOXX + 4);
+            RowN N{b.x, b.y, a.y, c.x};
+#pragma unroll
+            for(int l = 0; l < S; ++l)
+            {
+                // N is row (r0 - S + i - l) of level l. With three rows of level l, its middle row yields level l+1.
+                if(i < 2 * (l + 1))
+                {
+                    // not enough rows yet: just roll
+                    U[l][0] = C[l].x;
+                    U[l][1] = C[l].y;
+                    C[l] = N;
+                    break;
+                }
+                double vx = ftcs(C[l].x, C[l].l, C[l].y, U[l][0], N.x, A.k, A.rX, A.rY);
+                double vy = ftcs(C[l].y, C[l].x, C[l].r, U[l][1], N.y, A.k, A.rX, A.rY);
+                U[l][0] = C[l].x;
+                U[l][1] = C[l].y;
+                C[l] = N;
+                int32_t const gj = y0 + r0 - S + i - (l + 1); // row of the new level-(l+1) values
+                if(l + 1 < S)
+                {
+                    if constexpr(EDGE)
+                    {
+                        bool const jCore = gj >= 1 && gj <= int32_t(A.ny);
+                        if(!(jCore && gi >= 1 && gi <= int32_t(A.nx)))
+                            vx = ringOrZeroN(A, gj, gi, A.tf[l]);
+                        if(!(jCore && gi + 1 >= 1 && gi + 1 <= int32_t(A.nx)))
+                            vy = ringOrZeroN(A, gj, gi + 1, A.tf[l]);
+                    }
+                    N = RowN{vx, vy, shflUp1(vy), shflDown1(vx)};
+                }
+                else
+                {
+                    // level S: the output row
+                    double* out = A.dst + int64_t(gj) * int64_t(A.pitchElems) + gi;
+                    if constexpr(!EDGE)
+                    {
+                        if(storeLane)
+                            stg2<1>(out, vx, vy);
+                    }
+                    else if(storeLane && gj >= 0 && gj <= int32_t(A.ny) + 1)
+                    {
+                        bool const jCore = gj >= 1 && gj <= int32_t(A.ny);
+                        bool w0 = false, w1 = false;
+                        if(gi >= 0 && gi <= int32_t(A.nx) + 1)
+                        {
+                            bool const iCore = gi >= 1 && gi <= int32_t(A.nx);
+                            if(!(jCore && iCore))
+                                vx = ringOrZeroN(A, gj, gi, A.tf[S - 1]);
+                            w0 = jCore || iCore; // core or ring; only the four corners have neither
+                        }
+                        if(gi + 1 >= 0 && gi + 1 <= int32_t(A.nx) + 1)
+                        {
+                            bool const iCore = gi + 1 >= 1 && gi + 1 <= int32_t(A.nx);
+                            if(!(jCore && iCore))
+                                vy = ringOrZeroN(A, gj, gi + 1, A.tf[S - 1]);
+                            w1 = jCore || iCore;
+                        }
+                        if(w0 && w1)
+                            stg2<1>(out, vx, vy);
+                        else if(w0)
+                            out[0] = vx;
+                        else if(w1)
+                            out[1] = vy;
+                    }
+                }
+            }
+        }
+    }
+
+    template<int S, int RPT, int NWY>
+    __global__ void __launch_bounds__(32 * StepNGeom<S>::NWX * NWY) heatStepNKernel(const __grid_constant__ CUtensorMap mapSrc, HeatNArgs const A)
+    {
+        using G = StepNGeom<S>;
+        constexpr int TYT = NWY * RPT;
+        constexpr uint32_t kBoxBytes = uint32_t(G::BOXX) * (TYT + 2 * S) * 8;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t full;
+        int const tid = threadIdx.x;
+        uint32_t const ty = blockIdx.x / A.tilesX;
+        uint32_t const tx = blockIdx.x - ty * A.tilesX;
+        int32_t const y0 = int32_t(ty) * TYT, x0 = int32_t(tx) * G::WOUT;
+        if(tid == 0)
+        {
+            mbarInit(&full, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbarExpectTx(&full, kBoxBytes);
+            tmaLoad2d(smem, &mapSrc, x0 - G::M - 2, y0 - S, &full);
+        }
+        __syncthreads();
+        mbarWait(&full, 0);
+
+        int const warp = tid / 32, lane = tid % 32;
+        int const wx = warp % G::NWX, wy = warp / G::NWX;
+        double const* box = reinterpret_cast<double const*>(smem);
+        // every intermediate cell this tile computes -- rows y0-(S-1) .. y0+TYT+S-2, columns x0-M .. x0+WOUT+M-1 -- is a
+        // core cell
+        bool const interior = y0 - (S - 1) >= 1 && y0 + TYT + S - 2 <= int32_t(A.ny) && x0 - G::M >= 1
+                              && x0 + G::WOUT + G::M - 1 <= int32_t(A.nx);
+        if(interior)
+            stepNRows<S, RPT, NWY, false>(A, box, y0, x0, wx, wy, lane);
+        else
+            stepNRows<S, RPT, NWY, true>(A, box, y0, x0, wx, wy, lane);
+    }
+
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
     // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
     __global__ void __launch_bounds__(256) heatBoundaryKernel(HeatArgs const A)
@@ -760,7 +951,7 @@ namespace
     }
 
     // TMA descriptor of one padded field: rows x (nx+2) doubles at `pitchBytes`, box BOX_X x boxY
-    bool encodeFieldMap(EncodeTiledFn enc, CUtensorMap* map, double* base, size_t pitchBytes, uint64_t rows, uint32_t nx, int boxY)
+    bool encodeFieldMap(EncodeTiledFn enc, CUtensorMap* map, double* base, size_t pitchBytes, uint64_t rows, uint32_t nx, int boxY, int boxX = BOX_X)
     {
         int64_t const promoSel = b200::tune("heat.l2promo", 256);
         CUtensorMapL2promotion const promo = promoSel == 0     ? CU_TENSOR_MAP_L2_PROMOTION_NONE
@@ -769,7 +960,7 @@ namespace
                                                                : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         cuuint64_t const dims[2] = {cuuint64_t(nx) + 2, cuuint64_t(rows)};
         cuuint64_t const strides[1] = {cuuint64_t(pitchBytes)};
-        cuuint32_t const box[2] = {cuuint32_t(BOX_X), cuuint32_t(boxY)};
+        cuuint32_t const box[2] = {cuuint32_t(boxX), cuuint32_t(boxY)};
         cuuint32_t const estr[2] = {1, 1};
         return enc(
                    map,
@@ -800,6 +991,8 @@ struct b200_heat2d_plan_st
     CUtensorMap map[2];
     CUtensorMap map2[2]; // two-level kernel: box (TYT+4) x 132 at tile height map2Tyt (0 = not built yet)
     int map2Tyt = 0;
+    CUtensorMap mapN[2]; // N-level kernel: box keyed by mapNKey = levels * 1000 + tile rows (0 = not built yet)
+    int mapNKey = 0;
     uint32_t padY = 1; // 1: reference layout (ny+2 rows); 2: row slab with ghost rows two deep (ny+4 rows)
     // fused halo exchange (b200_heat2d_plan_set_halo)
     bool hasHalo = false;
@@ -865,6 +1058,8 @@ extern "C"
             {
                 if(e == cudaSuccess)
                     e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                // (measured: forcing three 72 KB tiles per SM -- 80 registers + the maximum shared-memory carve-out -- is
+                // 2 % slower than the two the driver's default carve-out admits: profiles/r01/heat_step2_probe*.log)
             };
             optIn(heatStepKernel<0, 8>);
             optIn(heatStepKernel<1, 8>);
@@ -875,6 +1070,11 @@ extern "C"
             optIn(heatStep2Kernel<1, 32, 32>, Step2Geom<32>::kBoxBytes);
             optIn(heatStep2Kernel<1, 64, 16>, Step2Geom<64>::kBoxBytes);
             optIn(heatStep2Kernel<1, 64, 32>, Step2Geom<64>::kBoxBytes);
+            optIn(heatStepNKernel<3, 16, 4>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<3, 16, 2>, StepNGeom<3>::BOXX * (32 + 6) * 8);
+            optIn(heatStepNKernel<3, 32, 2>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<4, 16, 4>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<4, 32, 2>, StepNGeom<4>::BOXX * (64 + 8) * 8);
             if(e != cudaSuccess)
             {
                 cudaFree(plan->sx);
@@ -1172,6 +1372,78 @@ extern "C"
         // ghost sides need the neighbour's intermediate level: stand-alone fields only (slabs: b200_heat2d_step2_halo_f64)
         B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo && plan->padY == 1, B200_EINVAL);
         return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, 0);
+    }
+
+    int b200_heat2d_stepn_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        int levels,
+        double const* time_factors)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors, B200_EINVAL);
+        B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
+        B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo && plan->padY == 1, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(plan->dev));
+        int const rpt = int(b200::tune("heat.stepn_rpt", 16));
+        int const nwy = int(b200::tune("heat.stepn_nwy", 2));
+        int const tyt = rpt * nwy;
+        int const boxX = levels == 3 ? StepNGeom<3>::BOXX : StepNGeom<4>::BOXX;
+        int const wout = levels == 3 ? StepNGeom<3>::WOUT : StepNGeom<4>::WOUT;
+        int const key = levels * 1000 + tyt;
+        if(plan->mapNKey != key)
+        {
+            EncodeTiledFn const enc = encoder();
+            if(!enc)
+                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+            for(int b = 0; b < 2; ++b)
+                if(!encodeFieldMap(enc, &plan->mapN[b], plan->u[b], plan->pitchBytes, uint64_t(plan->ny) + 2, plan->nx, tyt + 2 * levels, boxX))
+                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (N-level box)", __FILE__, __LINE__);
+            plan->mapNKey = key;
+        }
+        HeatNArgs A{};
+        A.dst = plan->u[1 - src_index];
+        A.pitchElems = plan->pitchBytes / 8;
+        A.ny = plan->ny;
+        A.nx = plan->nx;
+        A.tilesX = (plan->nx + 2 + uint32_t(wout) - 1) / uint32_t(wout);
+        A.rX = rx;
+        A.rY = ry;
+        A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
+        for(int l = 0; l < levels; ++l)
+            A.tf[l] = time_factors[l];
+        A.sx = plan->sx;
+        A.sy = plan->sy;
+        uint64_t const tilesY = (uint64_t(plan->ny) + 2 + uint64_t(tyt) - 1) / uint64_t(tyt);
+        uint64_t const grid = tilesY * A.tilesX;
+        B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
+        auto const s = reinterpret_cast<cudaStream_t>(stream);
+        size_t const smemBytes = size_t(boxX) * size_t(tyt + 2 * levels) * 8;
+        auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->mapN[src_index], A); };
+        switch(levels * 10000 + rpt * 100 + nwy)
+        {
+        case 31604:
+            launch(heatStepNKernel<3, 16, 4>, 256);
+            break;
+        case 31602:
+            launch(heatStepNKernel<3, 16, 2>, 128);
+            break;
+        case 33202:
+            launch(heatStepNKernel<3, 32, 2>, 128);
+            break;
+        case 41604:
+            launch(heatStepNKernel<4, 16, 4>, 256);
+            break;
+        case 43202:
+            launch(heatStepNKernel<4, 32, 2>, 128);
+            break;
+        default:
+            return b200::fail(B200_EINVAL, "heat.stepn_rpt/heat.stepn_nwy: supported 16/4, 16/2 (3 levels), 32/2", __FILE__, __LINE__);
+        }
+        B200_LAUNCH_CHECK();
+        return 0;
     }
 
     int b200_heat2d_step2_halo_f64(

@@ -86,25 +86,35 @@ class Heat2D:
         self.queue.wait()
         self.cur = 0
 
-    def step(self, n: int = 1, *, fuse: bool = True) -> None:
-        """n FTCS steps. `fuse` (stand-alone fields): pairs of steps go through ONE launch that keeps the intermediate
-        time level in registers (b200_heat2d_step2_f64: half the HBM traffic, same bits); an odd step runs alone.
-        NB after a fused pair the current field is in the buffer one swap -- not two -- away."""
+    #: time levels per launch that `step(n, fuse=True)` aims for (1..4); tests and tools override it per call
+    DEFAULT_FUSE = 3  # measured best at 16384^2: 1 -> 623, 2 -> 318, 3 -> 212, 4 -> 224 us per step (profiles/r01)
+
+    def step(self, n: int = 1, *, fuse=True) -> None:
+        """n FTCS steps. `fuse` (stand-alone fields): up to `fuse` steps (True = DEFAULT_FUSE, False = 1) go through ONE
+        launch that keeps the intermediate time levels in registers -- b200_heat2d_step2_f64 (2 levels) or
+        b200_heat2d_stepn_f64 (3, 4): HBM traffic of one step, same bits. A remainder runs in shallower launches.
+        NB after a fused launch the current field is in the buffer one swap away, whatever the number of levels."""
         lib = _lib.load()
-        fuse = fuse and self.edges == EDGE_ALL
+        depth = self.DEFAULT_FUSE if fuse is True else (1 if fuse is False else int(fuse))
+        if not 1 <= depth <= 4:
+            raise B200Error(-1, "heat2d: between 1 and 4 time levels per launch")
+        if self.edges != EDGE_ALL:
+            depth = 1
         done = 0
         while done < n:
-            if fuse and n - done >= 2:
-                tf1 = time_factor(self.step_index + 1, self.dt)
-                tf2 = time_factor(self.step_index + 2, self.dt)
-                check(lib.b200_heat2d_step2_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tf1, tf2))
-                self.step_index += 2
-                done += 2
+            k = min(depth, n - done)
+            if k > 2 and n - done - k == 1:
+                k -= 1  # 4 = 2 + 2 rather than 3 + 1
+            tfs = [time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
+            if k == 1:
+                check(lib.b200_heat2d_step_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tfs[0]))
+            elif k == 2:
+                check(lib.b200_heat2d_step2_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tfs[0], tfs[1]))
             else:
-                self.step_index += 1
-                done += 1
-                tf = time_factor(self.step_index, self.dt)
-                check(lib.b200_heat2d_step_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tf))
+                arr = (C.c_double * k)(*tfs)
+                check(lib.b200_heat2d_stepn_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, k, arr))
+            self.step_index += k
+            done += k
             self.cur ^= 1  # std::swap(uNextBufAcc, uCurrBufAcc), heatEquation2D.cpp:181
         self.queue._after_enqueue()
 

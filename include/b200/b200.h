@@ -305,6 +305,11 @@ extern "C"
      * level is unchanged, so the field is bit-identical to two b200_heat2d_step_f64 calls. Stand-alone fields only
      * (plan `edges` == B200_EDGE_ALL, no halo): a decomposed tile would need ghost cells two deep. */
     int b200_heat2d_step2_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor_1, double time_factor_2);
+    /* `levels` (3 or 4) steps in one launch: deeper temporal blocking. Threads compute only their own column pair per level and
+     * take the horizontal neighbours from adjacent lanes by warp shuffle (no recomputation, no shared-memory round trip);
+     * time_factors[l] is the boundary factor of the l-th level of the launch (time_factors[levels-1] the result's).
+     * Same conditions and the same bit-identical result as b200_heat2d_step2_f64. */
+    int b200_heat2d_stepn_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors);
     /* Restrict a step to a row/column window of OUTPUT cells [j0,j1) x [i0,i1) in padded coordinates
      * (used to split interior / edge strips for halo overlap). */
     int b200_heat2d_step_window_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t j0, uint32_t j1, uint32_t i0, uint32_t i1);

@@ -31,10 +31,11 @@ def _init(ny, nx, dx, dy):
 SHAPES = [(64, 64), (1, 1), (1, 7), (9, 1), (16, 16), (33, 129), (31, 127), (100, 257), (256, 1024), (515, 1030)]
 
 
-@pytest.mark.parametrize("fuse", [False, True], ids=["one_step_per_launch", "two_steps_per_launch"])
+@pytest.mark.parametrize("fuse", [1, 2, 3, 4], ids=lambda k: f"{k}_levels_per_launch")
 @pytest.mark.parametrize("shape", SHAPES)
 def test_heat2d_bit_exact_vs_oracle(gpu, shape, fuse):
-    """25 steps: 25 one-step launches, or 12 two-step launches (b200_heat2d_step2_f64) + 1 one-step launch."""
+    """25 steps: 25 one-step launches; 12 two-level launches (b200_heat2d_step2_f64) + 1; 8 three-level launches
+    (b200_heat2d_stepn_f64) + 1; 6 four-level launches + 1."""
     ab, dev, queue = gpu
     ny, nx = shape
     dx, dy, dt = ol.heat_params(ny, nx)
@@ -63,6 +64,26 @@ def test_heat2d_two_step_kernel_every_tile_shape(gpu, tile):
     finally:
         ab.runtime.tune_set("heat.step2_ty", 64)
         ab.runtime.tune_set("heat.step2_rpt", 16)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("cfg", [(3, 16, 4), (3, 16, 2), (3, 32, 2), (4, 16, 4), (4, 32, 2)], ids=lambda c: f"levels{c[0]}_rpt{c[1]}_nwy{c[2]}")
+def test_heat2d_n_level_kernel_every_tile_shape(gpu, cfg):
+    """Every instantiation of the shuffle-exchange N-level kernel on a rough field with partial tiles on both axes."""
+    ab, dev, queue = gpu
+    levels, rpt, nwy = cfg
+    ny, nx = 203, 391
+    dx, dy, dt = ol.heat_params(ny, nx)
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=22).reshape(ny + 2, nx + 2)
+    steps = 2 * levels + 1
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    ab.runtime.tune_set("heat.stepn_rpt", rpt)
+    ab.runtime.tune_set("heat.stepn_nwy", nwy)
+    try:
+        got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
+    finally:
+        ab.runtime.tune_set("heat.stepn_rpt", 16)
+        ab.runtime.tune_set("heat.stepn_nwy", 2)
     assert got.tobytes() == want.tobytes()
 
 

@@ -35,13 +35,14 @@ def main():
     rng = np.random.default_rng(5)
     u0 = rng.uniform(-1, 1, (sy_ + 2, sx_ + 2))
     outs = []
-    for fuse in (False, True):
+    for fuse in (1, 2, 3, 4):
         h = ab.heat2d.Heat2D(q, sy_, sx_, dx, dy, dt)
         h.upload(u0)
-        h.step(7, fuse=fuse)
+        h.step(9, fuse=fuse)
         outs.append(h.download())
         h.close()
-    print("one-step vs two-step launches, 7 steps, 203x391 rough field: bit-identical =", outs[0].tobytes() == outs[1].tobytes())
+    print("1 / 2 / 3 / 4 levels per launch, 9 steps, 203x391 rough field: bit-identical =",
+          all(o.tobytes() == outs[0].tobytes() for o in outs[1:]))
 
     dx, dy = 1.0 / (nx + 1), 1.0 / (ny + 1)
     dt = 0.2 * min(dx * dx, dy * dy)
@@ -55,6 +56,12 @@ def main():
         ms2 = timed(q, dev, lambda: h.step(2))
         print(f"two steps per launch ty={ty:2d} rpt={rpt:2d} {ny}x{nx}: {ms2 * 1e3 / 2:8.1f} us/step  "
               f"{2 * 16.0 * ny * nx * 1e-9 / (ms2 * 1e-3):8.1f} GB/s algorithmic  ({ms2 * 1e3:.1f} us/launch, x{2 * ms1 / ms2:.2f})")
+    for levels, rpt, nwy in ((3, 16, 4), (3, 16, 2), (3, 32, 2), (4, 16, 4), (4, 32, 2)):
+        ab.runtime.tune_set("heat.stepn_rpt", rpt)
+        ab.runtime.tune_set("heat.stepn_nwy", nwy)
+        msn = timed(q, dev, lambda: h.step(levels, fuse=levels))
+        print(f"{levels} steps per launch rpt={rpt:2d} nwy={nwy} {ny}x{nx}: {msn * 1e3 / levels:8.1f} us/step  "
+              f"{levels * 16.0 * ny * nx * 1e-9 / (msn * 1e-3):8.1f} GB/s algorithmic  ({msn * 1e3:.1f} us/launch, x{levels * ms1 / msn:.2f})")
     h.close()
 
 

@@ -9,7 +9,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'launch__registers_per_thread', 'launch__grid_size',
         'launch__block_size', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__occupancy_limit_registers',
-        'launch__occupancy_limit_shared_mem', 'smsp__inst_executed.sum']
+        'launch__occupancy_limit_shared_mem', 'smsp__inst_executed.sum',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'sm__warps_active.avg.per_cycle_active', 'launch__occupancy_limit_blocks', 'launch__occupancy_limit_warps']
 
 
 def summarise(path):
