@@ -715,16 +715,29 @@ namespace
         static constexpr int BOXX = WOUT + 2 * M + 4; // + M each side + 2 each side so that pairs stay 16-byte aligned
     };
 
+    // Rows of the array: [0, ny + 2 padY). padY = 1: the reference layout. padY = S: a row slab whose ghost rows are S deep
+    // (see Heat2Args); columns always carry the one-cell ring.
     struct HeatNArgs
     {
         double* dst;
         size_t pitchElems;
         uint32_t ny, nx;
+        int32_t loY, hiY; // first / last core row = padY, ny + padY - 1
         uint32_t tilesX;
         double k, rX, rY;
         double tf[kMaxLevels]; // tf[l-1]: time factor of the l-th level of this launch
         double const* sx;
         double const* sy;
+        int32_t ghostTop, ghostBottom; // 1: that side has a neighbour
+        uint32_t nTop, nBot, tyBot; // tile order: strip tile rows first, as in Heat2Args
+        // ---- fused halo exchange of a slab; null / 0 for a stand-alone field
+        double* peerDst[2];
+        uint32_t* peerFlag[2];
+        uint32_t* myFlags;
+        uint32_t* stripCounter;
+        uint32_t* status;
+        uint32_t stripTiles;
+        uint32_t step; // 1-based index of this launch
     };
 
     struct RowN
@@ -742,14 +755,16 @@ namespace
         return __shfl_down_sync(0xffffffffu, v, 1);
     }
 
-    // exactSolution at a ring cell, 0 anywhere else that is not a core cell (never consumed); j, i may be out of range
-    __device__ __forceinline__ double ringOrZeroN(HeatNArgs const& A, int32_t j, int32_t i, double tf)
+    // A cell of a level that the stencil does not produce: exactSolution where it is a ring cell -- the physical ring
+    // rows over core columns, the ring columns over the rows [jLo, jHi] on which this level is defined (core rows, and for a
+    // slab the neighbour's rows it still needs) --, 0 anywhere else (never consumed). j, i may be out of range.
+    __device__ __forceinline__ double ringOrZeroN(HeatNArgs const& A, int32_t j, int32_t i, int32_t jLo, int32_t jHi, double tf)
     {
         bool const iCore = i >= 1 && i <= int32_t(A.nx);
-        bool const jCore = j >= 1 && j <= int32_t(A.ny);
-        bool const rowRing = j == 0 || j == int32_t(A.ny) + 1;
+        bool const jDefined = j >= jLo && j <= jHi;
+        bool const rowRing = (j == A.loY - 1 && !A.ghostTop) || (j == A.hiY + 1 && !A.ghostBottom);
         bool const colRing = i == 0 || i == int32_t(A.nx) + 1;
-        if((rowRing && iCore) || (colRing && jCore))
+        if((rowRing && iCore) || (colRing && jDefined))
             return __dmul_rn(tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
         return 0.0;
     }
@@ -792,15 +807,18 @@ namespace
                 U[l][1] = C[l].y;
                 C[l] = N;
                 int32_t const gj = y0 + r0 - S + i - (l + 1); // row of the new level-(l+1) values
+                // rows on which level l+1 is defined: the core rows, and on a side with a neighbour the S-(l+1) rows
+                // beyond them that deeper levels still need
+                int32_t const jLo = A.loY - (S - (l + 1)) * A.ghostTop, jHi = A.hiY + (S - (l + 1)) * A.ghostBottom;
                 if(l + 1 < S)
                 {
                     if constexpr(EDGE)
                     {
-                        bool const jCore = gj >= 1 && gj <= int32_t(A.ny);
-                        if(!(jCore && gi >= 1 && gi <= int32_t(A.nx)))
-                            vx = ringOrZeroN(A, gj, gi, A.tf[l]);
-                        if(!(jCore && gi + 1 >= 1 && gi + 1 <= int32_t(A.nx)))
-                            vy = ringOrZeroN(A, gj, gi + 1, A.tf[l]);
+                        bool const jDefined = gj >= jLo && gj <= jHi;
+                        if(!(jDefined && gi >= 1 && gi <= int32_t(A.nx)))
+                            vx = ringOrZeroN(A, gj, gi, jLo, jHi, A.tf[l]);
+                        if(!(jDefined && gi + 1 >= 1 && gi + 1 <= int32_t(A.nx)))
+                            vy = ringOrZeroN(A, gj, gi + 1, jLo, jHi, A.tf[l]);
                     }
                     N = RowN{vx, vy, shflUp1(vy), shflDown1(vx)};
                 }
@@ -813,22 +831,23 @@ namespace
                         if(storeLane)
                             stg2<1>(out, vx, vy);
                     }
-                    else if(storeLane && gj >= 0 && gj <= int32_t(A.ny) + 1)
+                    else if(storeLane)
                     {
-                        bool const jCore = gj >= 1 && gj <= int32_t(A.ny);
+                        bool const jCore = gj >= A.loY && gj <= A.hiY;
+                        bool const jRing = (gj == A.loY - 1 && !A.ghostTop) || (gj == A.hiY + 1 && !A.ghostBottom);
                         bool w0 = false, w1 = false;
-                        if(gi >= 0 && gi <= int32_t(A.nx) + 1)
+                        if((jCore || jRing) && gi >= 0 && gi <= int32_t(A.nx) + 1)
                         {
                             bool const iCore = gi >= 1 && gi <= int32_t(A.nx);
                             if(!(jCore && iCore))
-                                vx = ringOrZeroN(A, gj, gi, A.tf[S - 1]);
-                            w0 = jCore || iCore; // core or ring; only the four corners have neither
+                                vx = ringOrZeroN(A, gj, gi, jLo, jHi, A.tf[S - 1]);
+                            w0 = jCore || iCore; // core or ring; corners have neither
                         }
-                        if(gi + 1 >= 0 && gi + 1 <= int32_t(A.nx) + 1)
+                        if((jCore || jRing) && gi + 1 >= 0 && gi + 1 <= int32_t(A.nx) + 1)
                         {
                             bool const iCore = gi + 1 >= 1 && gi + 1 <= int32_t(A.nx);
                             if(!(jCore && iCore))
-                                vy = ringOrZeroN(A, gj, gi + 1, A.tf[S - 1]);
+                                vy = ringOrZeroN(A, gj, gi + 1, jLo, jHi, A.tf[S - 1]);
                             w1 = jCore || iCore;
                         }
                         if(w0 && w1)
@@ -837,6 +856,26 @@ namespace
                             out[0] = vx;
                         else if(w1)
                             out[1] = vy;
+                        // fused halo exchange: my first / last S core rows (ring columns included) are the neighbour's ghost
+                        // rows; slabs have equal heights, so my row gj is the upper neighbour's row gj + ny and the lower
+                        // neighbour's row gj - ny
+                        if(jCore && (w0 || w1))
+                        {
+                            double* peer = nullptr;
+                            if(A.peerDst[0] != nullptr && gj < A.loY + S)
+                                peer = A.peerDst[0] + int64_t(gj + int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
+                            else if(A.peerDst[1] != nullptr && gj > A.hiY - S)
+                                peer = A.peerDst[1] + int64_t(gj - int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
+                            if(peer != nullptr)
+                            {
+                                if(w0 && w1)
+                                    stg2<0>(peer, vx, vy);
+                                else if(w0)
+                                    peer[0] = vx;
+                                else
+                                    peer[1] = vy;
+                            }
+                        }
                     }
                 }
             }
@@ -852,13 +891,39 @@ namespace
         extern __shared__ __align__(128) unsigned char smem[];
         __shared__ uint64_t full;
         int const tid = threadIdx.x;
-        uint32_t const ty = blockIdx.x / A.tilesX;
-        uint32_t const tx = blockIdx.x - ty * A.tilesX;
+        uint32_t const ord = blockIdx.x / A.tilesX; // tile row in launch order: strips first
+        uint32_t const tx = blockIdx.x - ord * A.tilesX;
+        bool const strip = ord < A.nTop + A.nBot;
+        uint32_t const ty = ord < A.nTop ? ord : (strip ? A.tyBot + (ord - A.nTop) : A.nTop + (ord - A.nTop - A.nBot));
         int32_t const y0 = int32_t(ty) * TYT, x0 = int32_t(tx) * G::WOUT;
         if(tid == 0)
         {
             mbarInit(&full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if(strip && A.myFlags != nullptr)
+            {
+                // as in heatStep2Kernel: the ghost rows this strip tile reads have arrived (and the neighbours are done
+                // reading the ones this launch overwrites) once their flags show the previous launch
+                for(int side = 0; side < 2; ++side)
+                {
+                    if(A.peerDst[side] == nullptr)
+                        continue;
+                    uint32_t seen = 0, spins = 0;
+                    for(;;)
+                    {
+                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
+                        if(seen + 1u >= A.step)
+                            break;
+                        if(++spins > 2000000u)
+                        {
+                            atomicExch(A.status, 1u + uint32_t(side));
+                            break;
+                        }
+                        __nanosleep(1000);
+                    }
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             mbarExpectTx(&full, kBoxBytes);
             tmaLoad2d(smem, &mapSrc, x0 - G::M - 2, y0 - S, &full);
         }
@@ -869,13 +934,31 @@ namespace
         int const wx = warp % G::NWX, wy = warp / G::NWX;
         double const* box = reinterpret_cast<double const*>(smem);
         // every intermediate cell this tile computes -- rows y0-(S-1) .. y0+TYT+S-2, columns x0-M .. x0+WOUT+M-1 -- is a
-        // core cell
-        bool const interior = y0 - (S - 1) >= 1 && y0 + TYT + S - 2 <= int32_t(A.ny) && x0 - G::M >= 1
+        // core cell, and no row of the tile travels to a neighbour
+        bool const interior = !strip && y0 - (S - 1) >= A.loY && y0 + TYT + S - 2 <= A.hiY && x0 - G::M >= 1
                               && x0 + G::WOUT + G::M - 1 <= int32_t(A.nx);
         if(interior)
             stepNRows<S, RPT, NWY, false>(A, box, y0, x0, wx, wy, lane);
         else
             stepNRows<S, RPT, NWY, true>(A, box, y0, x0, wx, wy, lane);
+
+        if(strip && A.stripCounter != nullptr)
+        {
+            __syncthreads();
+            if(tid == 0)
+            {
+                __threadfence_system();
+                uint32_t const done = atomicAdd(A.stripCounter, 1u);
+                if(done == A.stripTiles - 1u)
+                {
+                    __threadfence_system();
+                    *A.stripCounter = 0u;
+                    for(int side = 0; side < 2; ++side)
+                        if(A.peerFlag[side] != nullptr)
+                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
+                }
+            }
+        }
     }
 
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
@@ -1074,6 +1157,7 @@ extern "C"
             optIn(heatStepNKernel<3, 16, 2>, StepNGeom<3>::BOXX * (32 + 6) * 8);
             optIn(heatStepNKernel<3, 32, 2>, StepNGeom<3>::BOXX * (64 + 6) * 8);
             optIn(heatStepNKernel<4, 16, 4>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<4, 16, 2>, StepNGeom<4>::BOXX * (32 + 8) * 8);
             optIn(heatStepNKernel<4, 32, 2>, StepNGeom<4>::BOXX * (64 + 8) * 8);
             if(e != cudaSuccess)
             {
@@ -1112,11 +1196,14 @@ extern "C"
         double const* sx_host,
         double const* sy_host,
         int edges,
+        uint32_t ghost_rows,
         b200_heat2d_plan_t* out)
     {
-        // a slab keeps the full width: left and right are physical boundaries; two border rows per side must be distinct
-        B200_REQUIRE((edges & B200_EDGE_LEFT) && (edges & B200_EDGE_RIGHT) && ny >= 4, B200_EINVAL);
-        return createPlan(dev, u0, u1, pitch_bytes, ny, nx, sx_host, sy_host, edges, 2, out);
+        // a slab keeps the full width: left and right are physical boundaries; the border rows sent up and down must be
+        // distinct rows
+        B200_REQUIRE((edges & B200_EDGE_LEFT) && (edges & B200_EDGE_RIGHT), B200_EINVAL);
+        B200_REQUIRE(ghost_rows >= 2 && ghost_rows <= uint32_t(kMaxLevels) && ny >= 2 * ghost_rows, B200_EINVAL);
+        return createPlan(dev, u0, u1, pitch_bytes, ny, nx, sx_host, sy_host, edges, ghost_rows, out);
     }
 
     int b200_heat2d_plan_destroy(b200_heat2d_plan_t plan)
@@ -1374,6 +1461,105 @@ extern "C"
         return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, 0);
     }
 
+    namespace
+    {
+        int launchStepN(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, double rx, double ry, int levels, double const* tfs, uint32_t haloStep)
+        {
+            B200_CUDA(cudaSetDevice(plan->dev));
+            int const rpt = int(b200::tune("heat.stepn_rpt", 16));
+            int const nwy = int(b200::tune("heat.stepn_nwy", 2));
+            int const tyt = rpt * nwy;
+            int const boxX = levels == 3 ? StepNGeom<3>::BOXX : StepNGeom<4>::BOXX;
+            int const wout = levels == 3 ? StepNGeom<3>::WOUT : StepNGeom<4>::WOUT;
+            uint32_t const rows = plan->ny + 2 * plan->padY;
+            int const key = levels * 1000 + tyt;
+            if(plan->mapNKey != key)
+            {
+                EncodeTiledFn const enc = encoder();
+                if(!enc)
+                    return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+                for(int b = 0; b < 2; ++b)
+                    if(!encodeFieldMap(enc, &plan->mapN[b], plan->u[b], plan->pitchBytes, rows, plan->nx, tyt + 2 * levels, boxX))
+                        return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (N-level box)", __FILE__, __LINE__);
+                plan->mapNKey = key;
+            }
+            HeatNArgs A{};
+            A.dst = plan->u[1 - src_index];
+            A.pitchElems = plan->pitchBytes / 8;
+            A.ny = plan->ny;
+            A.nx = plan->nx;
+            A.loY = int32_t(plan->padY);
+            A.hiY = int32_t(plan->ny + plan->padY - 1);
+            A.tilesX = (plan->nx + 2 + uint32_t(wout) - 1) / uint32_t(wout);
+            A.rX = rx;
+            A.rY = ry;
+            A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
+            for(int l = 0; l < levels; ++l)
+                A.tf[l] = tfs[l];
+            A.sx = plan->sx;
+            A.sy = plan->sy;
+            A.ghostTop = (plan->edges & B200_EDGE_TOP) ? 0 : 1;
+            A.ghostBottom = (plan->edges & B200_EDGE_BOTTOM) ? 0 : 1;
+            uint32_t const tilesY = (rows + uint32_t(tyt) - 1) / uint32_t(tyt);
+            // strip tile rows: tile row 0 (ghost rows 0..S-1, border rows S..2S-1) and the tile rows from the one holding the
+            // first of the last S core rows on (tile rows are at least 2S rows tall)
+            A.nTop = A.ghostTop ? 1u : 0u;
+            A.tyBot = A.ghostBottom ? uint32_t(A.hiY - levels + 1) / uint32_t(tyt) : tilesY;
+            if(A.tyBot < A.nTop)
+                A.tyBot = A.nTop;
+            A.nBot = tilesY - A.tyBot;
+            if(haloStep != 0)
+            {
+                int const dstIndex = 1 - src_index;
+                for(int side = 0; side < 2; ++side)
+                {
+                    A.peerDst[side] = plan->halo.peer_u[side][dstIndex];
+                    A.peerFlag[side] = plan->halo.peer_flag[side];
+                }
+                A.myFlags = plan->halo.my_flags;
+                A.stripCounter = plan->haloScratch;
+                A.status = plan->haloScratch + 1;
+                A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
+                A.step = haloStep;
+                int64_t const dbg = b200::tune("heat.halo_debug", 0);
+                if(dbg & 1)
+                    A.peerDst[0] = A.peerDst[1] = nullptr;
+                if(dbg & 2)
+                    A.myFlags = nullptr;
+            }
+            uint64_t const grid = uint64_t(tilesY) * A.tilesX;
+            B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
+            auto const s = reinterpret_cast<cudaStream_t>(stream);
+            size_t const smemBytes = size_t(boxX) * size_t(tyt + 2 * levels) * 8;
+            auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->mapN[src_index], A); };
+            switch(levels * 10000 + rpt * 100 + nwy)
+            {
+            case 31604:
+                launch(heatStepNKernel<3, 16, 4>, 256);
+                break;
+            case 31602:
+                launch(heatStepNKernel<3, 16, 2>, 128);
+                break;
+            case 33202:
+                launch(heatStepNKernel<3, 32, 2>, 128);
+                break;
+            case 41604:
+                launch(heatStepNKernel<4, 16, 4>, 256);
+                break;
+            case 41602:
+                launch(heatStepNKernel<4, 16, 2>, 128);
+                break;
+            case 43202:
+                launch(heatStepNKernel<4, 32, 2>, 128);
+                break;
+            default:
+                return b200::fail(B200_EINVAL, "heat.stepn_rpt/heat.stepn_nwy: supported 16/2, 16/4, 32/2", __FILE__, __LINE__);
+            }
+            B200_LAUNCH_CHECK();
+            return 0;
+        }
+    } // namespace
+
     int b200_heat2d_stepn_f64(
         b200_heat2d_plan_t plan,
         b200_stream_t stream,
@@ -1386,64 +1572,24 @@ extern "C"
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors, B200_EINVAL);
         B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
         B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo && plan->padY == 1, B200_EINVAL);
-        B200_CUDA(cudaSetDevice(plan->dev));
-        int const rpt = int(b200::tune("heat.stepn_rpt", 16));
-        int const nwy = int(b200::tune("heat.stepn_nwy", 2));
-        int const tyt = rpt * nwy;
-        int const boxX = levels == 3 ? StepNGeom<3>::BOXX : StepNGeom<4>::BOXX;
-        int const wout = levels == 3 ? StepNGeom<3>::WOUT : StepNGeom<4>::WOUT;
-        int const key = levels * 1000 + tyt;
-        if(plan->mapNKey != key)
-        {
-            EncodeTiledFn const enc = encoder();
-            if(!enc)
-                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
-            for(int b = 0; b < 2; ++b)
-                if(!encodeFieldMap(enc, &plan->mapN[b], plan->u[b], plan->pitchBytes, uint64_t(plan->ny) + 2, plan->nx, tyt + 2 * levels, boxX))
-                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (N-level box)", __FILE__, __LINE__);
-            plan->mapNKey = key;
-        }
-        HeatNArgs A{};
-        A.dst = plan->u[1 - src_index];
-        A.pitchElems = plan->pitchBytes / 8;
-        A.ny = plan->ny;
-        A.nx = plan->nx;
-        A.tilesX = (plan->nx + 2 + uint32_t(wout) - 1) / uint32_t(wout);
-        A.rX = rx;
-        A.rY = ry;
-        A.k = 1.0 - 2.0 * rx - 2.0 * ry; // StencilKernel.hpp:84, as in baseArgs
-        for(int l = 0; l < levels; ++l)
-            A.tf[l] = time_factors[l];
-        A.sx = plan->sx;
-        A.sy = plan->sy;
-        uint64_t const tilesY = (uint64_t(plan->ny) + 2 + uint64_t(tyt) - 1) / uint64_t(tyt);
-        uint64_t const grid = tilesY * A.tilesX;
-        B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
-        auto const s = reinterpret_cast<cudaStream_t>(stream);
-        size_t const smemBytes = size_t(boxX) * size_t(tyt + 2 * levels) * 8;
-        auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->mapN[src_index], A); };
-        switch(levels * 10000 + rpt * 100 + nwy)
-        {
-        case 31604:
-            launch(heatStepNKernel<3, 16, 4>, 256);
-            break;
-        case 31602:
-            launch(heatStepNKernel<3, 16, 2>, 128);
-            break;
-        case 33202:
-            launch(heatStepNKernel<3, 32, 2>, 128);
-            break;
-        case 41604:
-            launch(heatStepNKernel<4, 16, 4>, 256);
-            break;
-        case 43202:
-            launch(heatStepNKernel<4, 32, 2>, 128);
-            break;
-        default:
-            return b200::fail(B200_EINVAL, "heat.stepn_rpt/heat.stepn_nwy: supported 16/4, 16/2 (3 levels), 32/2", __FILE__, __LINE__);
-        }
-        B200_LAUNCH_CHECK();
-        return 0;
+        return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, 0);
+    }
+
+    int b200_heat2d_stepn_halo_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        int levels,
+        double const* time_factors,
+        uint32_t step)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors && step >= 1, B200_EINVAL);
+        B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
+        // the ghost rows of the slab must be exactly as deep as the launch advances
+        B200_REQUIRE(plan->hasHalo && plan->padY == uint32_t(levels), B200_EINVAL);
+        return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, step);
     }
 
     int b200_heat2d_step2_halo_f64(

@@ -124,46 +124,55 @@ class HeatTile:
 class _SlabInfo:
     """What connect_over_process_group / connect_in_process need to know about a slab (the Tile fields they use)."""
 
-    def __init__(self, rank: int, world: int, ny: int, nx: int):
-        self.rank, self.world, self.ny, self.nx = rank, world, ny, nx
+    def __init__(self, rank: int, world: int, ny: int, nx: int, ghost: int):
+        self.rank, self.world, self.ny, self.nx, self.ghost = rank, world, ny, nx, ghost
         self.neighbours = {"top": None if rank == 0 else rank - 1, "bottom": None if rank == world - 1 else rank + 1,
                            "left": None, "right": None}
         self.edges = decomp.EDGE_LEFT | decomp.EDGE_RIGHT | (decomp.EDGE_TOP if rank == 0 else 0) | (
             decomp.EDGE_BOTTOM if rank == world - 1 else 0)
-        self.shape = (ny + 4, nx + 2)
-        self.j_offset = rank * ny  # local row j is global padded row j_offset + j - 1
+        self.shape = (ny + 2 * ghost, nx + 2)
+        self.j_offset = rank * ny  # local row j is global padded row j_offset + j - (ghost - 1)
 
 
 class HeatSlab(HeatTile):
-    """One rank's ROW SLAB of the field, advanced TWO time levels per launch and per exchange
-    (b200_heat2d_slab_plan_create / b200_heat2d_step2_halo_f64, include/b200/b200.h): the temporal blocking of the
-    stand-alone two-level kernel carried to several GPUs. Ghost rows are two deep, so the local array is
-    (ny+4) x (nx+2): rows 0,1 / ny+2,ny+3 are ghosts (or ring + unused on a physical side), core rows are 2..ny+1.
-    Same wiring calls as HeatTile (export / open_peer / connect, connect_over_process_group, connect_in_process)."""
+    """One rank's ROW SLAB of the field, advanced `levels` (2, 3 or 4) time levels per launch and per exchange
+    (b200_heat2d_slab_plan_create + b200_heat2d_step2_halo_f64 / b200_heat2d_stepn_halo_f64, include/b200/b200.h): the
+    temporal blocking of the stand-alone kernels carried to several GPUs. Ghost rows are G = `levels` deep, so the
+    local array is (ny+2G) x (nx+2): rows 0..G-1 / ny+G.. are ghosts (or ring + unused rows on a physical side), core
+    rows are G..ny+G-1. Same wiring calls as HeatTile (export / open_peer / connect, connect_over_process_group,
+    connect_in_process)."""
 
-    def __init__(self, queue: Queue, rank: int, world: int, NY: int, NX: int, dt: Optional[float] = None):
+    DEFAULT_LEVELS = 3
+
+    def __init__(self, queue: Queue, rank: int, world: int, NY: int, NX: int, dt: Optional[float] = None,
+                 levels: Optional[int] = None):
         import math
 
-        if NY % world != 0 or NY // world < 4:
-            raise B200Error(-1, f"heat slabs: {NY} core rows do not divide into {world} slabs of at least 4 rows")
+        G = self.DEFAULT_LEVELS if levels is None else int(levels)
+        if G not in (2, 3, 4):
+            raise B200Error(-1, "heat slabs advance 2, 3 or 4 time levels per launch")
+        if NY % world != 0 or NY // world < 2 * G:
+            raise B200Error(-1, f"heat slabs: {NY} core rows do not divide into {world} slabs of at least {2 * G} rows")
         self.queue, self.dev = queue, queue.dev
-        self.NY, self.NX = NY, NX
+        self.NY, self.NX, self.levels = NY, NX, G
         ny, nx = NY // world, NX
-        self.tile = _SlabInfo(rank, world, ny, nx)
+        self.tile = _SlabInfo(rank, world, ny, nx, G)
         self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)
         self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
         if heat2d.stability_ratio(self.dx, self.dy, self.dt) > 1.0:
             raise B200Error(-1, "Stability condition check failed")
         self.rx, self.ry = self.dt / (self.dx * self.dx), self.dt / (self.dy * self.dy)
-        self.bufs = [Buf(self.dev, np.float64, (ny + 4, nx + 2), queue, ipc=True) for _ in range(2)]
+        self.bufs = [Buf(self.dev, np.float64, (ny + 2 * G, nx + 2), queue, ipc=True) for _ in range(2)]
         self.cur, self.step_index, self.launch_index = 0, 0, 0
         pi = math.pi
+        self.g0 = self.tile.j_offset - (G - 1)  # global padded row of local row 0 (may be negative: unused rows)
         self.sx = np.array([math.sin(pi * (i * self.dx)) for i in range(nx + 2)], dtype=np.float64)
-        self.sy = np.array([math.sin(pi * ((self.tile.j_offset + j - 1) * self.dy)) for j in range(ny + 4)], dtype=np.float64)
+        self.sy = np.array([math.sin(pi * ((self.g0 + j) * self.dy)) for j in range(ny + 2 * G)], dtype=np.float64)
         plan = C.c_void_p()
         lib = _lib.load()
         check(lib.b200_heat2d_slab_plan_create(self.dev.idx, self.bufs[0].ptr, self.bufs[1].ptr, self.bufs[0].pitch_bytes,
-                                               ny, nx, self.sx.ctypes.data, self.sy.ctypes.data, self.tile.edges, C.byref(plan)))
+                                               ny, nx, self.sx.ctypes.data, self.sy.ctypes.data, self.tile.edges, G,
+                                               C.byref(plan)))
         self.plan = plan.value
         self.flags = Buf(self.dev, np.uint32, 16, ipc=True)
         check(lib.b200_memset_async(self.dev.idx, self.flags.ptr, 0, 64, queue.handle))
@@ -174,12 +183,11 @@ class HeatSlab(HeatTile):
 
     # ---- data
     def window(self, global_field: np.ndarray) -> np.ndarray:
-        """This slab's (ny+4) x (nx+2) window of a global (NY+2) x (NX+2) padded field; rows outside the field are 0."""
-        ny = self.tile.ny
-        out = np.zeros((ny + 4, self.NX + 2))
-        g0 = self.tile.j_offset - 1  # global row of local row 0
-        lo, hi = max(g0, 0), min(g0 + ny + 4, self.NY + 2)
-        out[lo - g0 : hi - g0, :] = global_field[lo:hi, :]
+        """This slab's (ny+2G) x (nx+2) window of a global (NY+2) x (NX+2) padded field; rows outside the field are 0."""
+        rows = self.tile.shape[0]
+        out = np.zeros((rows, self.NX + 2))
+        lo, hi = max(self.g0, 0), min(self.g0 + rows, self.NY + 2)
+        out[lo - self.g0 : hi - self.g0, :] = global_field[lo:hi, :]
         return out
 
     def initial_field(self) -> np.ndarray:
@@ -190,25 +198,33 @@ class HeatSlab(HeatTile):
     def upload(self, local_field: np.ndarray) -> None:
         local_field = np.ascontiguousarray(local_field, dtype=np.float64)
         if local_field.shape != self.tile.shape:
-            raise B200Error(-1, "heat slab: field must be (ny+4) x (nx+2)")
+            raise B200Error(-1, "heat slab: field must be (ny+2G) x (nx+2)")
         memcpy(self.queue, self.bufs[0], local_field)
         memcpy(self.queue, self.bufs[1], local_field)
         self.queue.wait()
         self.cur = 0
 
-    def step(self, n: int = 2) -> None:
-        """n FTCS steps, n even: n/2 launches, each advancing two time levels and exchanging two ghost rows per side."""
-        if n % 2 != 0:
-            raise B200Error(-1, "heat slabs advance two time levels per launch: the number of steps must be even")
+    def step(self, n: Optional[int] = None) -> None:
+        """n FTCS steps (default: one launch), n a multiple of `levels`: n/levels launches, each advancing `levels` time
+        levels and exchanging that many ghost rows per side."""
+        G = self.levels
+        n = G if n is None else n
+        if n % G != 0:
+            raise B200Error(-1, f"this heat slab advances {G} time levels per launch: the number of steps must be a multiple of {G}")
         if not self.connected:
             raise B200Error(-1, "HeatSlab.step before connect()")
         lib = _lib.load()
-        for _ in range(n // 2):
+        for _ in range(n // G):
             self.launch_index += 1
-            tf1 = heat2d.time_factor(self.step_index + 1, self.dt)
-            tf2 = heat2d.time_factor(self.step_index + 2, self.dt)
-            check(lib.b200_heat2d_step2_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tf1, tf2, self.launch_index))
-            self.step_index += 2
+            tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(G)]
+            if G == 2:
+                check(lib.b200_heat2d_step2_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tfs[0], tfs[1],
+                                                     self.launch_index))
+            else:
+                arr = (C.c_double * G)(*tfs)
+                check(lib.b200_heat2d_stepn_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, G, arr,
+                                                     self.launch_index))
+            self.step_index += G
             self.cur ^= 1
         self.queue._after_enqueue()
 
@@ -224,13 +240,17 @@ class HeatSlab(HeatTile):
         self.queue.wait()
         return out
 
+    def owned_rows(self) -> tuple[int, int]:
+        """[j0, j1) of the local rows this slab OWNS: its core rows, plus the physical ring row on a boundary side."""
+        G, ny = self.levels, self.tile.ny
+        j0 = G - 1 if self.tile.edges & decomp.EDGE_TOP else G
+        j1 = ny + G + 1 if self.tile.edges & decomp.EDGE_BOTTOM else ny + G
+        return j0, j1
+
     def stitch(self, global_out: np.ndarray, local_field: np.ndarray) -> None:
-        """Writes the rows this slab OWNS (core rows, plus the physical ring row on a boundary side) into the global
-        (NY+2) x (NX+2) field."""
-        ny, g0 = self.tile.ny, self.tile.j_offset - 1
-        j0 = 1 if self.tile.edges & decomp.EDGE_TOP else 2
-        j1 = ny + 3 if self.tile.edges & decomp.EDGE_BOTTOM else ny + 2
-        global_out[g0 + j0 : g0 + j1, :] = local_field[j0:j1, :]
+        """Writes the rows this slab owns into the global (NY+2) x (NX+2) field."""
+        j0, j1 = self.owned_rows()
+        global_out[self.g0 + j0 : self.g0 + j1, :] = local_field[j0:j1, :]
 
     def close(self) -> None:
         lib = _lib.load()

@@ -348,10 +348,11 @@ def run_ours(args):
             lib.b200_memset2d_async(dev.idx, h.bufs[0].ptr, h.bufs[0].pitch_bytes, 0, (NX + 2) * 8, NY + 2, q.handle)
             lib.b200_memset2d_async(dev.idx, h.bufs[1].ptr, h.bufs[1].pitch_bytes, 0, (NX + 2) * 8, NY + 2, q.handle)
             record("heat2d_f64", timed(lambda: h.step(1), max(20, K), 5), 16.0 * NY * NX)
-            # two time levels per launch (b200_heat2d_step2_f64): the same 16 B per cell per step of ALGORITHMIC bytes,
-            # half of them actually moved, so the fraction of the HBM peak may exceed 1
-            record("heat2d_f64_two_steps_per_launch", timed(lambda: h.step(2), max(20, K), 5), 2 * 16.0 * NY * NX)
-            kernels["heat2d_f64_two_steps_per_launch"]["ms_per_step"] = round(kernels["heat2d_f64_two_steps_per_launch"]["ms"] / 2, 4)
+            # 2 and 3 time levels per launch (b200_heat2d_step2_f64 / b200_heat2d_stepn_f64): the same 16 B per cell per step
+            # of ALGORITHMIC bytes, a half / a third of them actually moved, so the fraction of the HBM peak exceeds 1
+            for G in (2, 3):
+                record(f"heat2d_f64_{G}_steps_per_launch", timed(lambda: h.step(G, fuse=G), max(20, K), 5), G * 16.0 * NY * NX)
+                kernels[f"heat2d_f64_{G}_steps_per_launch"]["ms_per_step"] = round(kernels[f"heat2d_f64_{G}_steps_per_launch"]["ms"] / G, 4)
             h.close()
         else:
             from alpaka_b200 import decomp, multi
@@ -383,18 +384,20 @@ def run_ours(args):
             multi.connect_over_process_group(slab, dist)
             slab.upload(slab.initial_field())
             barrier()
-            ms_slab = timed(lambda: slab.step(2), max(50, K), 5)
+            G = slab.levels
+            ms_slab = timed(lambda: slab.step(G), max(50, K), 5)
             assert slab.status() == 0, "heat slab flag wait timed out"
-            record("heat2d_f64_two_steps_per_launch", ms_slab, 2 * 16.0 * NY * NX / world)
-            kernels["heat2d_f64_two_steps_per_launch"].update(
-                scaling="strong", ms_per_step=round(ms_slab / 2, 4),
-                decomposition=f"{world} row slabs of {NY // world}x{NX}, ghost rows two deep, fused P2P halo")
+            name_s = f"heat2d_f64_{G}_steps_per_launch"
+            record(name_s, ms_slab, G * 16.0 * NY * NX / world)
+            kernels[name_s].update(
+                scaling="strong", ms_per_step=round(ms_slab / G, 4),
+                decomposition=f"{world} row slabs of {NY // world}x{NX}, ghost rows {G} deep, fused P2P halo")
             local = slab.download()
             tmax = slab.step_index * slab.dt
             exact = math.exp(-math.pi * math.pi * tmax) * (slab.sx[None, :] + slab.sy[:, None])
-            err = float(np.max(np.abs(local[2:-2, 1:-1] - exact[2:-2, 1:-1])))
+            err = float(np.max(np.abs(local[G:-G, 1:-1] - exact[G:-G, 1:-1])))
             assert err < 1e-4, f"slab-decomposed heat field deviates from the analytic solution: {err}"
-            kernels["heat2d_f64_two_steps_per_launch"]["max_abs_error_vs_analytic"] = err
+            kernels[name_s]["max_abs_error_vs_analytic"] = err
             slab.close()
             if not args.heat:
                 # BASELINE.json configs[4]: 65536^2 weak-scaled over 8 GPUs = 16384 x 32768 core cells per GPU; the same
@@ -416,12 +419,12 @@ def run_ours(args):
                 multi.connect_over_process_group(sw, dist)
                 sw.upload(sw.initial_field())
                 barrier()
-                ms_sw = timed(lambda: sw.step(2), max(20, K), 5)
+                ms_sw = timed(lambda: sw.step(G), max(20, K), 5)
                 assert sw.status() == 0, "heat slab flag wait timed out"
-                record("heat2d_f64_weak_two_steps_per_launch", ms_sw, 2 * 16.0 * NYw * NXw / world)
-                kernels["heat2d_f64_weak_two_steps_per_launch"].update(
-                    scaling="weak", ms_per_step=round(ms_sw / 2, 4),
-                    decomposition=f"{NYw}x{NXw} global, {world} row slabs of {NYw // world}x{NXw}, ghost rows two deep")
+                record(f"heat2d_f64_weak_{G}_steps_per_launch", ms_sw, G * 16.0 * NYw * NXw / world)
+                kernels[f"heat2d_f64_weak_{G}_steps_per_launch"].update(
+                    scaling="weak", ms_per_step=round(ms_sw / G, 4),
+                    decomposition=f"{NYw}x{NXw} global, {world} row slabs of {NYw // world}x{NXw}, ghost rows {G} deep")
                 sw.close()
         q.wait()
 

@@ -336,17 +336,19 @@ extern "C"
     } b200_heat2d_halo;
     int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo);
     int b200_heat2d_step_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t step);
-    /* ---- Row-SLAB decomposition with TWO time levels per launch and per exchange (new). Temporal blocking needs ghost
-     * cells two deep; with row slabs (every rank keeps the full width) only rows are exchanged, they are contiguous, and
-     * no diagonal neighbour exists. Array layout of a slab: (ny+4) x (nx+2) doubles -- rows 0,1 and ny+2,ny+3 are ghost
-     * rows on a side with a neighbour; on a physical side row 1 / ny+2 is the ring and row 0 / ny+3 is unused; core rows
-     * are 2..ny+1; columns carry the reference's one-cell ring. sy_host has ny+4 entries (sy[j] for local row j).
-     * `edges` must contain LEFT and RIGHT; ny >= 4; all slabs of a field have the same ny, nx and pitch.
+    /* ---- Row-SLAB decomposition with G = 2, 3 or 4 time levels per launch and per exchange (new). Temporal blocking
+     * needs ghost cells G deep; with row slabs (every rank keeps the full width) only rows are exchanged, they are
+     * contiguous, and no diagonal neighbour exists. Array layout of a slab: (ny+2G) x (nx+2) doubles -- rows 0..G-1 and
+     * ny+G..ny+2G-1 are ghost rows on a side with a neighbour; on a physical side row G-1 / ny+G is the ring and the rows
+     * beyond it are unused; core rows are G..ny+G-1; columns carry the reference's one-cell ring. sy_host has ny+2G
+     * entries (sy[j] for local row j, ghost rows included: their ring-column cells are boundary cells of the
+     * neighbour's rows). `edges` must contain LEFT and RIGHT; ny >= 2G; all slabs of a field have the same ny, nx, pitch.
      * b200_heat2d_plan_set_halo wires the neighbours (sides 0 = top, 1 = bottom; left/right stay NULL). One launch of
-     * b200_heat2d_step2_halo_f64 reads level s (ghost rows included) from buffer `src_index`, writes level s+2 of the
-     * core rows and physical ring into the other buffer, stores its first / last two core rows straight into the
-     * neighbours' ghost rows (peer stores from registers) and publishes `step` (1-based launch index) in their flag
-     * words; strip tiles come first and wait for the neighbours' flags of launch step-1, as in the one-level form. */
+     * b200_heat2d_step2_halo_f64 (G = 2) / b200_heat2d_stepn_halo_f64 (levels = G = 3 or 4) reads level s (ghost rows
+     * included) from buffer `src_index`, writes level s+G of the core rows and physical ring into the other buffer,
+     * stores its first / last G core rows straight into the neighbours' ghost rows (peer stores from registers) and
+     * publishes `step` (1-based launch index) in their flag words; strip tiles come first and wait for the
+     * neighbours' flags of launch step-1, as in the one-level form. */
     int b200_heat2d_slab_plan_create(
         int dev,
         double* u0,
@@ -355,10 +357,12 @@ extern "C"
         uint32_t ny,
         uint32_t nx,
         double const* sx_host, /* nx+2 */
-        double const* sy_host, /* ny+4 */
+        double const* sy_host, /* ny+2*ghost_rows */
         int edges,
+        uint32_t ghost_rows, /* G */
         b200_heat2d_plan_t* out);
     int b200_heat2d_step2_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor_1, double time_factor_2, uint32_t step);
+    int b200_heat2d_stepn_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors, uint32_t step);
     /* 0, or 1 + side of the first flag wait that timed out (a neighbour stopped making progress). Synchronous. */
     int b200_heat2d_halo_status(b200_heat2d_plan_t plan, uint32_t* status);
 

@@ -92,32 +92,29 @@ def main():
     dist.barrier()
     runner.close()
 
-    # ---- row slabs, two time levels per launch and per exchange (ghost rows two deep), IPC peer pointers
+    # ---- row slabs, 2 and 3 time levels per launch and per exchange (ghost rows that deep), IPC peer pointers
     NYs, NXs, steps2 = 160 * world, 900, 24
-    slab = multi.HeatSlab(q, rank, world, NYs, NXs)
-    multi.connect_over_process_group(slab, dist)
     dxs, dys, dts = ol.heat_params(NYs, NXs)
     u0s = np.empty((NYs + 2, NXs + 2))
     ol.oracle().orc_heat2d_init(P(u0s), NYs, NXs, NXs + 2, dxs, dys)
-    slab.upload(slab.window(u0s))
-    dist.barrier()
-    slab.step(steps2)
-    q.wait()
-    assert slab.status() == 0, f"rank {rank}: slab flag wait timed out"
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object((rank, slab.download()), gathered, dst=0)
-    if rank == 0:
-        out = np.full((NYs + 2, NXs + 2), np.nan)
-        ny_s = NYs // world
-        for rk, f in gathered:
-            g0 = rk * ny_s - 1
-            j0 = 1 if rk == 0 else 2
-            j1 = ny_s + 3 if rk == world - 1 else ny_s + 2
-            out[g0 + j0 : g0 + j1, :] = f[j0:j1, :]
-        want = ol.orc_heat_run(u0s, 1, steps2, dxs, dys, dts)
-        assert out.tobytes() == want.tobytes(), "slab-decomposed two-level heat differs from the undecomposed oracle"
-    dist.barrier()
-    slab.close()
+    want_s = ol.orc_heat_run(u0s, 1, steps2, dxs, dys, dts) if rank == 0 else None
+    for levels in (2, 3):
+        slab = multi.HeatSlab(q, rank, world, NYs, NXs, levels=levels)
+        multi.connect_over_process_group(slab, dist)
+        slab.upload(slab.window(u0s))
+        dist.barrier()
+        slab.step(steps2)
+        q.wait()
+        assert slab.status() == 0, f"rank {rank}: slab flag wait timed out"
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((slab.g0, slab.owned_rows(), slab.download()), gathered, dst=0)
+        if rank == 0:
+            out = np.full((NYs + 2, NXs + 2), np.nan)
+            for g0, (j0, j1), f in gathered:
+                out[g0 + j0 : g0 + j1, :] = f[j0:j1, :]
+            assert out.tobytes() == want_s.tobytes(), f"slab-decomposed {levels}-level heat differs from the undecomposed oracle"
+        dist.barrier()
+        slab.close()
     if rank == 0:
         print(f"MP_WORKER_OK {world}", flush=True)
     dist.destroy_process_group()

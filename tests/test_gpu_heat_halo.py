@@ -85,18 +85,20 @@ def test_single_tile_halo_launch_equals_plain_step(gpu):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# Row slabs advanced TWO time levels per launch and per exchange (b200_heat2d_step2_halo_f64): ghost rows two deep.
-def run_slabs(ab, dev, NY, NX, world, steps, u0):
+# Row slabs advanced 2, 3 or 4 time levels per launch and per exchange (b200_heat2d_step2_halo_f64 /
+# b200_heat2d_stepn_halo_f64): ghost rows as deep as the launch advances.
+def run_slabs(ab, dev, NY, NX, world, steps, u0, levels):
     from alpaka_b200 import multi
 
     queues = [ab.Queue(dev) for _ in range(world)]
-    runners = [multi.HeatSlab(q, r, world, NY, NX) for r, q in enumerate(queues)]
+    runners = [multi.HeatSlab(q, r, world, NY, NX, levels=levels) for r, q in enumerate(queues)]
     multi.connect_in_process(runners)
     for r in runners:
         r.upload(r.window(u0))
-    for _ in range(steps // 2):
+    assert steps % levels == 0
+    for _ in range(steps // levels):
         for r in runners:
-            r.step(2)
+            r.step(levels)
     for q in queues:
         q.wait()
     out = np.full((NY + 2, NX + 2), np.nan)
@@ -113,8 +115,9 @@ def run_slabs(ab, dev, NY, NX, world, steps, u0):
 SLAB_CASES = [(2, 20, 96), (3, 61, 200), (2, 127, 391), (4, 200, 700), (1, 150, 300), (8, 64, 256)]
 
 
+@pytest.mark.parametrize("levels", [2, 3, 4])
 @pytest.mark.parametrize("case", SLAB_CASES, ids=lambda c: f"{c[0]}slabs_of_{c[1]}x{c[2]}")
-def test_slabs_two_levels_per_launch_equal_undecomposed(gpu, case):
+def test_slabs_fused_levels_equal_undecomposed(gpu, case, levels):
     ab, dev, _ = gpu
     world, ny, NX = case
     NY, steps = ny * world, 12
@@ -122,19 +125,20 @@ def test_slabs_two_levels_per_launch_equal_undecomposed(gpu, case):
     u0 = np.empty((NY + 2, NX + 2))
     ol.oracle().orc_heat2d_init(P(u0), NY, NX, NX + 2, dx, dy)
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
-    got = run_slabs(ab, dev, NY, NX, world, steps, u0)
+    got = run_slabs(ab, dev, NY, NX, world, steps, u0, levels)
     assert got.tobytes() == want.tobytes()
 
 
-def test_slabs_rough_field_bit_exact(gpu):
+@pytest.mark.parametrize("levels", [2, 3, 4])
+def test_slabs_rough_field_bit_exact(gpu, levels):
     """A rough field exercises every neighbour term across the slab borders (the analytic field is smooth)."""
     ab, dev, _ = gpu
-    world, ny, NX, steps = 3, 70, 263, 8
+    world, ny, NX, steps = 3, 70, 263, 12
     NY = ny * world
     dx, dy, dt = ol.heat_params(NY, NX)
     u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=33).reshape(NY + 2, NX + 2)
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
-    got = run_slabs(ab, dev, NY, NX, world, steps, u0)
+    got = run_slabs(ab, dev, NY, NX, world, steps, u0, levels)
     assert got.tobytes() == want.tobytes()
 
 
@@ -142,11 +146,11 @@ def test_slab_argument_errors(gpu):
     ab, dev, queue = gpu
     from alpaka_b200 import multi
 
-    with pytest.raises(ab.B200Error):  # odd number of steps
-        s = multi.HeatSlab(queue, 0, 1, 64, 64)
+    with pytest.raises(ab.B200Error):  # not a multiple of the levels per launch
+        s = multi.HeatSlab(queue, 0, 1, 64, 64, levels=3)
         multi.connect_in_process([s])
         try:
-            s.step(3)
+            s.step(4)
         finally:
             s.close()
     with pytest.raises(ab.B200Error):  # rows do not divide
