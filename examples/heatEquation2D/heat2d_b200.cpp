@@ -10,7 +10,8 @@
 //                     ALPAKA_B200_NATIVE=0)
 //   --mode=fused      per step: one launch of the fused native kernel (alpaka::b200::Heat2DStepper)
 //   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
-//                     (Heat2DStepper::steps -> b200_heat2d_step2_f64; an odd last step runs alone); same bits
+//   --mode=fused3     per THREE steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
+//                     a remainder runs in shallower launches); same bits
 //   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
 //   --output=<file>   dump the final (ny+2) x (nx+2) field, unpadded, for the parity tests
 #include "../common/cli.hpp"
@@ -140,11 +141,12 @@ auto main(int argc, char** argv) -> int
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);
         }
-        else if(mode == "fused2")
+        else if(mode == "fused2" || mode == "fused3")
         {
+            int const depth = mode == "fused2" ? 2 : 3;
             alpaka::b200::Heat2DStepper stepper(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
-            stepper.steps(computeQueue, numTimeSteps);
-            launches = numTimeSteps / 2 + numTimeSteps % 2;
+            stepper.steps(computeQueue, numTimeSteps, depth);
+            launches = (numTimeSteps + depth - 1) / depth;
             alpaka::wait(computeQueue);
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);

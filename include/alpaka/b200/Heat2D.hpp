@@ -95,17 +95,41 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
-        //! `n` steps, pairwise fused where possible
+        //! `levels` (3 or 4) fused steps in ONE launch (b200_heat2d_stepn_f64: own column pair per thread and level, the
+        //! horizontal neighbours by warp shuffle); same bits, the roles of the buffers swap ONCE.
         template<typename TQueue>
-        void steps(TQueue& queue, std::uint32_t n, bool fuse = true)
+        void stepN(TQueue& queue, int levels)
         {
-            while(n >= 2 && fuse)
+            constexpr double pi = math::constants::pi;
+            double tf[4] = {};
+            for(int l = 0; l < levels && l < 4; ++l)
+                tf[l] = std::exp(-pi * pi * ((m_step + 1u + static_cast<std::uint32_t>(l)) * m_dt));
+            check(b200_heat2d_stepn_f64(m_plan, queue.getNativeHandle(), m_cur, m_rX, m_rY, levels, tf));
+            m_step += static_cast<std::uint32_t>(levels);
+            m_cur ^= 1;
+            queue.afterEnqueue();
+        }
+
+        //! `n` steps with up to `depth` (1..4; measured best: 3) time levels per launch; a remainder runs in shallower
+        //! launches (4 = 2 + 2 rather than 3 + 1)
+        template<typename TQueue>
+        void steps(TQueue& queue, std::uint32_t n, int depth = 3)
+        {
+            if(depth < 1 || depth > 4)
+                throw std::runtime_error("Heat2DStepper::steps: between 1 and 4 time levels per launch");
+            while(n > 0)
             {
-                step2(queue);
-                n -= 2;
+                auto k = static_cast<std::uint32_t>(depth) < n ? static_cast<std::uint32_t>(depth) : n;
+                if(k > 2 && n - k == 1)
+                    --k;
+                if(k == 1)
+                    step(queue);
+                else if(k == 2)
+                    step2(queue);
+                else
+                    stepN(queue, static_cast<int>(k));
+                n -= k;
             }
-            while(n-- > 0)
-                step(queue);
         }
 
         //! 0 if the current field is bufA, 1 if it is bufB
