@@ -455,7 +455,8 @@ namespace
         uint32_t* stripCounter;
         uint32_t* status;
         uint32_t stripTiles;
-        uint32_t step; // 1-based index of this launch (it produces time level 2 * step)
+        uint32_t step; // 1-based index of this launch
+        uint32_t sendRows; // border rows stored into each neighbour = depth of the ghost rows (>= 2)
     };
 
     struct Row6
@@ -575,15 +576,15 @@ namespace
                     out[0] = v0;
                 else if(w1)
                     out[1] = v1;
-                // fused halo exchange: my first / last two core rows (ring columns included) are the neighbour's ghost
+                // fused halo exchange: my first / last `sendRows` core rows (ring columns included) are the neighbour's ghost
                 // rows; peer stores (NVLink) from the registers holding the fresh values. Slabs have equal heights, so
                 // my row gj is the upper neighbour's row gj + ny and the lower neighbour's row gj - ny.
                 if(jCore && (w0 || w1))
                 {
                     double* peer = nullptr;
-                    if(A.peerDst[0] != nullptr && gj <= A.loY + 1u)
+                    if(A.peerDst[0] != nullptr && gj < A.loY + A.sendRows)
                         peer = A.peerDst[0] + size_t(gj + A.ny) * A.pitchElems + gi;
-                    else if(A.peerDst[1] != nullptr && gj + 1u >= A.hiY)
+                    else if(A.peerDst[1] != nullptr && gj + A.sendRows > A.hiY)
                         peer = A.peerDst[1] + size_t(gj - A.ny) * A.pitchElems + gi;
                     if(peer != nullptr)
                     {
@@ -738,6 +739,7 @@ namespace
         uint32_t* status;
         uint32_t stripTiles;
         uint32_t step; // 1-based index of this launch
+        int32_t sendRows; // border rows stored into each neighbour = depth of the ghost rows (>= S)
     };
 
     struct RowN
@@ -856,15 +858,15 @@ namespace
                             out[0] = vx;
                         else if(w1)
                             out[1] = vy;
-                        // fused halo exchange: my first / last S core rows (ring columns included) are the neighbour's ghost
-                        // rows; slabs have equal heights, so my row gj is the upper neighbour's row gj + ny and the lower
+                        // fused halo exchange: my first / last `sendRows` core rows (ring columns included) are the neighbour's
+                        // ghost rows; slabs have equal heights, so my row gj is the upper neighbour's row gj + ny and the lower
                         // neighbour's row gj - ny
                         if(jCore && (w0 || w1))
                         {
                             double* peer = nullptr;
-                            if(A.peerDst[0] != nullptr && gj < A.loY + S)
+                            if(A.peerDst[0] != nullptr && gj < A.loY + A.sendRows)
                                 peer = A.peerDst[0] + int64_t(gj + int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
-                            else if(A.peerDst[1] != nullptr && gj > A.hiY - S)
+                            else if(A.peerDst[1] != nullptr && gj > A.hiY - A.sendRows)
                                 peer = A.peerDst[1] + int64_t(gj - int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
                             if(peer != nullptr)
                             {
@@ -1391,8 +1393,9 @@ extern "C"
             uint32_t const tilesY = (rows + uint32_t(tyt) - 1) / uint32_t(tyt);
             // strip tile rows: the one holding ghost rows 0,1 and border rows 2,3; the ones holding rows hiY-1.. (border and
             // ghost rows at the bottom). They come first in the launch so their rows travel while the interior is computed.
+            A.sendRows = plan->padY;
             A.nTop = A.ghostTop ? 1u : 0u;
-            A.tyBot = A.ghostBottom ? (A.hiY - 1u) / uint32_t(tyt) : tilesY;
+            A.tyBot = A.ghostBottom ? (A.hiY + 1u - plan->padY) / uint32_t(tyt) : tilesY;
             if(A.tyBot < A.nTop)
                 A.tyBot = A.nTop;
             A.nBot = tilesY - A.tyBot;
@@ -1503,8 +1506,9 @@ extern "C"
             uint32_t const tilesY = (rows + uint32_t(tyt) - 1) / uint32_t(tyt);
             // strip tile rows: tile row 0 (ghost rows 0..S-1, border rows S..2S-1) and the tile rows from the one holding the
             // first of the last S core rows on (tile rows are at least 2S rows tall)
+            A.sendRows = int32_t(plan->padY);
             A.nTop = A.ghostTop ? 1u : 0u;
-            A.tyBot = A.ghostBottom ? uint32_t(A.hiY - levels + 1) / uint32_t(tyt) : tilesY;
+            A.tyBot = A.ghostBottom ? uint32_t(A.hiY + 1 - int32_t(plan->padY)) / uint32_t(tyt) : tilesY;
             if(A.tyBot < A.nTop)
                 A.tyBot = A.nTop;
             A.nBot = tilesY - A.tyBot;
@@ -1587,8 +1591,8 @@ extern "C"
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors && step >= 1, B200_EINVAL);
         B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
-        // the ghost rows of the slab must be exactly as deep as the launch advances
-        B200_REQUIRE(plan->hasHalo && plan->padY == uint32_t(levels), B200_EINVAL);
+        // the ghost rows must be at least as deep as the launch advances (all of them are refreshed by every launch)
+        B200_REQUIRE(plan->hasHalo && plan->padY >= uint32_t(levels), B200_EINVAL);
         return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, step);
     }
 
@@ -1603,7 +1607,8 @@ extern "C"
         uint32_t step)
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && step >= 1, B200_EINVAL);
-        B200_REQUIRE(plan->hasHalo && plan->padY == 2, B200_EINVAL);
+        // the ghost rows must be at least as deep as the launch advances (all of them are refreshed by every launch)
+        B200_REQUIRE(plan->hasHalo && plan->padY >= 2, B200_EINVAL);
         return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, step);
     }
 

@@ -205,26 +205,32 @@ class HeatSlab(HeatTile):
         self.cur = 0
 
     def step(self, n: Optional[int] = None) -> None:
-        """n FTCS steps (default: one launch), n a multiple of `levels`: n/levels launches, each advancing `levels` time
-        levels and exchanging that many ghost rows per side."""
+        """n FTCS steps (default: one launch of `levels`): launches of `levels` time levels each, the remainder in
+        shallower ones (every launch refreshes all G ghost rows, so depths can be mixed; 4 = 2 + 2 rather than 3 + 1).
+        A slab cannot advance a single level: n = 1, or an odd n at levels = 2, is refused."""
         G = self.levels
         n = G if n is None else n
-        if n % G != 0:
-            raise B200Error(-1, f"this heat slab advances {G} time levels per launch: the number of steps must be a multiple of {G}")
+        if n < 0 or n == 1 or (G == 2 and n % 2 != 0):
+            raise B200Error(-1, f"a heat slab with ghost rows {G} deep cannot advance {n} step(s): launches cover 2..{G} time levels")
         if not self.connected:
             raise B200Error(-1, "HeatSlab.step before connect()")
         lib = _lib.load()
-        for _ in range(n // G):
+        left = n
+        while left > 0:
+            k = min(G, left)
+            if left - k == 1:
+                k -= 1
             self.launch_index += 1
-            tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(G)]
-            if G == 2:
+            tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
+            if k == 2:
                 check(lib.b200_heat2d_step2_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tfs[0], tfs[1],
                                                      self.launch_index))
             else:
-                arr = (C.c_double * G)(*tfs)
-                check(lib.b200_heat2d_stepn_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, G, arr,
+                arr = (C.c_double * k)(*tfs)
+                check(lib.b200_heat2d_stepn_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, k, arr,
                                                      self.launch_index))
-            self.step_index += G
+            self.step_index += k
+            left -= k
             self.cur ^= 1
         self.queue._after_enqueue()
 

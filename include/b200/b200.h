@@ -344,9 +344,10 @@ extern "C"
      * entries (sy[j] for local row j, ghost rows included: their ring-column cells are boundary cells of the
      * neighbour's rows). `edges` must contain LEFT and RIGHT; ny >= 2G; all slabs of a field have the same ny, nx, pitch.
      * b200_heat2d_plan_set_halo wires the neighbours (sides 0 = top, 1 = bottom; left/right stay NULL). One launch of
-     * b200_heat2d_step2_halo_f64 (G = 2) / b200_heat2d_stepn_halo_f64 (levels = G = 3 or 4) reads level s (ghost rows
-     * included) from buffer `src_index`, writes level s+G of the core rows and physical ring into the other buffer,
-     * stores its first / last G core rows straight into the neighbours' ghost rows (peer stores from registers) and
+     * b200_heat2d_step2_halo_f64 (2 levels) / b200_heat2d_stepn_halo_f64 (levels = 3 or 4), levels <= G, reads level s
+     * (ghost rows included) from buffer `src_index`, writes level s+levels of the core rows and physical ring into the
+     * other buffer, stores its first / last G core rows straight into the neighbours' ghost rows (peer stores from
+     * registers; always all G, so launches of different depths can follow each other, e.g. 1000 = 332 x 3 + 2 x 2) and
      * publishes `step` (1-based launch index) in their flag words; strip tiles come first and wait for the
      * neighbours' flags of launch step-1, as in the one-level form. */
     int b200_heat2d_slab_plan_create(
