@@ -111,6 +111,89 @@ def halo_slices(tile: Tile, side: str):
     raise ValueError(side)
 
 
+@dataclass(frozen=True)
+class Slab:
+    """One rank's ROW SLAB of the heat field for launches that advance several time levels: all NX columns, NY/world core
+    rows, ghost rows `ghost` deep. Local array (ny + 2*ghost) x (nx+2); local row j is global padded row g0 + j (g0 may be
+    negative on the first slab: rows outside the field are unused). Core rows are ghost .. ny+ghost-1; on a physical
+    side the row next to them is the ring. Field names shared with Tile where the wiring code needs them."""
+
+    rank: int
+    world: int
+    ny: int
+    nx: int
+    ghost: int
+    edges: int
+    neighbours: dict = field(default_factory=dict)
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self.ny + 2 * self.ghost, self.nx + 2
+
+    @property
+    def j_offset(self) -> int:
+        return self.rank * self.ny
+
+    @property
+    def g0(self) -> int:
+        return self.rank * self.ny - (self.ghost - 1)
+
+    def owned_rows(self) -> tuple[int, int]:
+        """[j0, j1) of the local rows this slab OWNS: its core rows, plus the physical ring row on a boundary side."""
+        j0 = self.ghost - 1 if self.edges & EDGE_TOP else self.ghost
+        j1 = self.ny + self.ghost + 1 if self.edges & EDGE_BOTTOM else self.ny + self.ghost
+        return j0, j1
+
+    def window(self, global_field):
+        """This slab's local array cut out of a global (NY+2) x (NX+2) padded field; rows outside the field are 0."""
+        import numpy as np
+
+        rows, NYp = self.shape[0], self.ny * self.world + 2
+        out = np.zeros((rows, self.nx + 2))
+        lo, hi = max(self.g0, 0), min(self.g0 + rows, NYp)
+        out[lo - self.g0 : hi - self.g0, :] = global_field[lo:hi, :]
+        return out
+
+    def stitch(self, global_out, local_field) -> None:
+        j0, j1 = self.owned_rows()
+        global_out[self.g0 + j0 : self.g0 + j1, :] = local_field[j0:j1, :]
+
+    def send_rows(self, side: str) -> slice:
+        """My `ghost` border core rows that become the ghost rows of the neighbour on `side` ('top' / 'bottom')."""
+        return slice(self.ghost, 2 * self.ghost) if side == "top" else slice(self.ny, self.ny + self.ghost)
+
+    def recv_rows(self, side: str) -> slice:
+        """My ghost rows on `side`."""
+        return slice(0, self.ghost) if side == "top" else slice(self.ny + self.ghost, self.ny + 2 * self.ghost)
+
+
+def slab_for(rank: int, world: int, NY: int, NX: int, ghost: int) -> Slab:
+    if ghost < 1 or world < 1 or not (0 <= rank < world):
+        raise ValueError("slab_for: bad arguments")
+    if NY % world != 0 or NY // world < 2 * ghost:
+        raise ValueError(f"slab_for: {NY} core rows do not divide into {world} slabs of at least {2 * ghost} rows")
+    nb = {"top": None if rank == 0 else rank - 1, "bottom": None if rank == world - 1 else rank + 1, "left": None, "right": None}
+    edges = EDGE_LEFT | EDGE_RIGHT | (EDGE_TOP if rank == 0 else 0) | (EDGE_BOTTOM if rank == world - 1 else 0)
+    return Slab(rank, world, NY // world, NX, ghost, edges, nb)
+
+
+def launch_schedule(n: int, depth: int, min_depth: int = 1) -> list[int]:
+    """Time levels per launch for n steps with at most `depth` levels per launch: greedy, but never a tail shallower
+    than needed (4 = 2 + 2 rather than 3 + 1). min_depth = 2 for slabs, which cannot advance a single level."""
+    if n < 0 or depth < max(1, min_depth):
+        raise ValueError("launch_schedule: bad arguments")
+    if min_depth > 1 and (n == 1 or (depth == 2 and n % 2 != 0)):
+        raise ValueError(f"{n} step(s) cannot be covered by launches of {min_depth}..{depth} time levels")
+    out, left = [], n
+    while left > 0:
+        k = min(depth, left)
+        if k > 2 and left - k == 1:
+            k -= 1
+        out.append(k)
+        left -= k
+    return out
+
+
 def combine_in_rank_order(parts):
     """The Dot / float-reduce exchange step: one scalar per rank, summed left to right in rank order so the result
     does not depend on the collective's internal order."""

@@ -100,11 +100,9 @@ class Heat2D:
             raise B200Error(-1, "heat2d: between 1 and 4 time levels per launch")
         if self.edges != EDGE_ALL:
             depth = 1
-        done = 0
-        while done < n:
-            k = min(depth, n - done)
-            if k > 2 and n - done - k == 1:
-                k -= 1  # 4 = 2 + 2 rather than 3 + 1
+        from .decomp import launch_schedule
+
+        for k in launch_schedule(n, depth):  # e.g. 3, 3, ..., then 4 = 2 + 2 rather than 3 + 1
             tfs = [time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
             if k == 1:
                 check(lib.b200_heat2d_step_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, tfs[0]))
@@ -114,7 +112,6 @@ class Heat2D:
                 arr = (C.c_double * k)(*tfs)
                 check(lib.b200_heat2d_stepn_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, k, arr))
             self.step_index += k
-            done += k
             self.cur ^= 1  # std::swap(uNextBufAcc, uCurrBufAcc), heatEquation2D.cpp:181
         self.queue._after_enqueue()
 

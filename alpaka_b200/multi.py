@@ -121,19 +121,6 @@ class HeatTile:
         self.flags.free()
 
 
-class _SlabInfo:
-    """What connect_over_process_group / connect_in_process need to know about a slab (the Tile fields they use)."""
-
-    def __init__(self, rank: int, world: int, ny: int, nx: int, ghost: int):
-        self.rank, self.world, self.ny, self.nx, self.ghost = rank, world, ny, nx, ghost
-        self.neighbours = {"top": None if rank == 0 else rank - 1, "bottom": None if rank == world - 1 else rank + 1,
-                           "left": None, "right": None}
-        self.edges = decomp.EDGE_LEFT | decomp.EDGE_RIGHT | (decomp.EDGE_TOP if rank == 0 else 0) | (
-            decomp.EDGE_BOTTOM if rank == world - 1 else 0)
-        self.shape = (ny + 2 * ghost, nx + 2)
-        self.j_offset = rank * ny  # local row j is global padded row j_offset + j - (ghost - 1)
-
-
 class HeatSlab(HeatTile):
     """One rank's ROW SLAB of the field, advanced `levels` (2, 3 or 4) time levels per launch and per exchange
     (b200_heat2d_slab_plan_create + b200_heat2d_step2_halo_f64 / b200_heat2d_stepn_halo_f64, include/b200/b200.h): the
@@ -151,12 +138,13 @@ class HeatSlab(HeatTile):
         G = self.DEFAULT_LEVELS if levels is None else int(levels)
         if G not in (2, 3, 4):
             raise B200Error(-1, "heat slabs advance 2, 3 or 4 time levels per launch")
-        if NY % world != 0 or NY // world < 2 * G:
-            raise B200Error(-1, f"heat slabs: {NY} core rows do not divide into {world} slabs of at least {2 * G} rows")
+        try:
+            self.tile = decomp.slab_for(rank, world, NY, NX, G)  # geometry: pure host logic, tested on CPU
+        except ValueError as e:
+            raise B200Error(-1, str(e)) from None
         self.queue, self.dev = queue, queue.dev
         self.NY, self.NX, self.levels = NY, NX, G
         ny, nx = NY // world, NX
-        self.tile = _SlabInfo(rank, world, ny, nx, G)
         self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)
         self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
         if heat2d.stability_ratio(self.dx, self.dy, self.dt) > 1.0:
@@ -165,7 +153,7 @@ class HeatSlab(HeatTile):
         self.bufs = [Buf(self.dev, np.float64, (ny + 2 * G, nx + 2), queue, ipc=True) for _ in range(2)]
         self.cur, self.step_index, self.launch_index = 0, 0, 0
         pi = math.pi
-        self.g0 = self.tile.j_offset - (G - 1)  # global padded row of local row 0 (may be negative: unused rows)
+        self.g0 = self.tile.g0  # global padded row of local row 0 (may be negative: unused rows)
         self.sx = np.array([math.sin(pi * (i * self.dx)) for i in range(nx + 2)], dtype=np.float64)
         self.sy = np.array([math.sin(pi * ((self.g0 + j) * self.dy)) for j in range(ny + 2 * G)], dtype=np.float64)
         plan = C.c_void_p()
@@ -184,11 +172,7 @@ class HeatSlab(HeatTile):
     # ---- data
     def window(self, global_field: np.ndarray) -> np.ndarray:
         """This slab's (ny+2G) x (nx+2) window of a global (NY+2) x (NX+2) padded field; rows outside the field are 0."""
-        rows = self.tile.shape[0]
-        out = np.zeros((rows, self.NX + 2))
-        lo, hi = max(self.g0, 0), min(self.g0 + rows, self.NY + 2)
-        out[lo - self.g0 : hi - self.g0, :] = global_field[lo:hi, :]
-        return out
+        return self.tile.window(global_field)
 
     def initial_field(self) -> np.ndarray:
         import math
@@ -210,16 +194,14 @@ class HeatSlab(HeatTile):
         A slab cannot advance a single level: n = 1, or an odd n at levels = 2, is refused."""
         G = self.levels
         n = G if n is None else n
-        if n < 0 or n == 1 or (G == 2 and n % 2 != 0):
-            raise B200Error(-1, f"a heat slab with ghost rows {G} deep cannot advance {n} step(s): launches cover 2..{G} time levels")
+        try:
+            schedule = decomp.launch_schedule(n, G, min_depth=2)
+        except ValueError as e:
+            raise B200Error(-1, f"heat slab with ghost rows {G} deep: {e}") from None
         if not self.connected:
             raise B200Error(-1, "HeatSlab.step before connect()")
         lib = _lib.load()
-        left = n
-        while left > 0:
-            k = min(G, left)
-            if left - k == 1:
-                k -= 1
+        for k in schedule:
             self.launch_index += 1
             tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
             if k == 2:
@@ -230,7 +212,6 @@ class HeatSlab(HeatTile):
                 check(lib.b200_heat2d_stepn_halo_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, k, arr,
                                                      self.launch_index))
             self.step_index += k
-            left -= k
             self.cur ^= 1
         self.queue._after_enqueue()
 
@@ -248,15 +229,11 @@ class HeatSlab(HeatTile):
 
     def owned_rows(self) -> tuple[int, int]:
         """[j0, j1) of the local rows this slab OWNS: its core rows, plus the physical ring row on a boundary side."""
-        G, ny = self.levels, self.tile.ny
-        j0 = G - 1 if self.tile.edges & decomp.EDGE_TOP else G
-        j1 = ny + G + 1 if self.tile.edges & decomp.EDGE_BOTTOM else ny + G
-        return j0, j1
+        return self.tile.owned_rows()
 
     def stitch(self, global_out: np.ndarray, local_field: np.ndarray) -> None:
         """Writes the rows this slab owns into the global (NY+2) x (NX+2) field."""
-        j0, j1 = self.owned_rows()
-        global_out[self.g0 + j0 : self.g0 + j1, :] = local_field[j0:j1, :]
+        self.tile.stitch(global_out, local_field)
 
     def close(self) -> None:
         lib = _lib.load()

@@ -181,3 +181,157 @@ def test_decomposed_heat_and_dot_over_gloo(tmp_path, world, NY, NX):
     dots = [float(np.load(tmp_path / f"dot{r}.npy")[0]) for r in range(world)]
     assert len(set(dots)) == 1
     assert abs(dots[0] - d_orc) <= 1e-12 * float(np.sum(np.abs(a * b)))
+
+
+# ------------------------------------------------------------------------------------------------ row slabs, several time levels per exchange
+@pytest.mark.parametrize("n,depth,min_depth", [(1000, 3, 2), (10, 3, 2), (13, 4, 2), (12, 2, 2), (7, 3, 1), (5, 1, 1), (4, 3, 1), (0, 3, 2), (2, 4, 2)])
+def test_launch_schedule_covers_the_steps(n, depth, min_depth):
+    sched = decomp.launch_schedule(n, depth, min_depth)
+    assert sum(sched) == n and all(min_depth <= k <= depth for k in sched)
+    assert len(sched) <= -(-n // depth) + 1  # at most one launch more than the minimum
+
+
+def test_launch_schedule_known_answers_and_refusals():
+    assert decomp.launch_schedule(1000, 3, 2) == [3] * 332 + [2, 2]
+    assert decomp.launch_schedule(4, 3) == [2, 2] and decomp.launch_schedule(7, 4) == [4, 3]
+    for bad in ((1, 3, 2), (3, 2, 2)):  # a slab cannot advance a single level
+        with pytest.raises(ValueError):
+            decomp.launch_schedule(*bad)
+
+
+@pytest.mark.parametrize("world,ghost", [(1, 2), (2, 2), (2, 3), (4, 3), (8, 4)])
+def test_slabs_cover_the_field_once_and_windows_round_trip(world, ghost):
+    NY, NX = 8 * ghost * world, 40
+    field = np.arange((NY + 2) * (NX + 2), dtype=np.float64).reshape(NY + 2, NX + 2)
+    owner = np.full((NY + 2, NX + 2), -1.0)
+    out = np.full((NY + 2, NX + 2), np.nan)
+    slabs = [decomp.slab_for(r, world, NY, NX, ghost) for r in range(world)]
+    for s in slabs:
+        w = s.window(field)
+        assert w.shape == s.shape == (NY // world + 2 * ghost, NX + 2)
+        j0, j1 = s.owned_rows()
+        assert (owner[s.g0 + j0 : s.g0 + j1] == -1).all(), "two slabs own the same row"
+        s.stitch(owner, np.full(s.shape, float(s.rank)))
+        s.stitch(out, w)
+        for side, other in (("top", "bottom"), ("bottom", "top")):
+            nb = s.neighbours[side]
+            assert (nb is None) == bool(s.edges & {"top": 1, "bottom": 2}[side])
+            if nb is not None:
+                assert slabs[nb].neighbours[other] == s.rank
+                # what I send up/down is exactly what the neighbour holds in its ghost rows on the opposite side
+                assert w[s.send_rows(side)].tobytes() == slabs[nb].window(field)[slabs[nb].recv_rows(other)].tobytes()
+        assert s.neighbours["left"] is None and s.neighbours["right"] is None and s.edges & 4 and s.edges & 8
+    assert (owner >= 0).all() and out.tobytes() == field.tobytes()
+    with pytest.raises(ValueError):
+        decomp.slab_for(0, 3, 64, 8, 2)  # rows do not divide
+    with pytest.raises(ValueError):
+        decomp.slab_for(0, 2, 8, 8, 3)  # slabs shallower than two ghost depths
+
+
+def numpy_slab_launch(u, slab, first_step, levels, dx, dy, dt):
+    """`levels` FTCS steps of one slab without communication, the way the fused kernels do it: level l is produced on the
+    core rows plus the (levels - l) rows beyond them that deeper levels need on a side with a neighbour; ring columns of
+    those rows and the physical ring rows take the analytic boundary value of that level. Ghost rows keep level 0."""
+    G, ny = slab.ghost, slab.ny
+    rX, rY = dt / (dx * dx), dt / (dy * dy)
+    k = 1.0 - 2.0 * rX - 2.0 * rY
+    pi = math.pi
+    sx = np.array([math.sin(pi * (i * dx)) for i in range(slab.nx + 2)])
+    sy = np.array([math.sin(pi * ((slab.g0 + j) * dy)) for j in range(ny + 2 * G)])
+    g_top, g_bot = (0 if slab.edges & decomp.EDGE_TOP else 1), (0 if slab.edges & decomp.EDGE_BOTTOM else 1)
+    cur = u
+    for lvl in range(1, levels + 1):
+        tf = math.exp(-pi * pi * ((first_step + lvl - 1) * dt))
+        lo, hi = G - (levels - lvl) * g_top, ny + G - 1 + (levels - lvl) * g_bot  # rows on which this level is defined
+        nxt = cur.copy()
+        rows = slice(lo, hi + 1)
+        c, l, r_ = cur[rows, 1:-1], cur[rows, :-2], cur[rows, 2:]
+        up, dn = cur[lo - 1 : hi, 1:-1], cur[lo + 1 : hi + 2, 1:-1]
+        nxt[rows, 1:-1] = (((c * k + l * rX) + r_ * rX) + up * rY) + dn * rY
+        nxt[rows, 0] = tf * (sx[0] + sy[rows])
+        nxt[rows, -1] = tf * (sx[-1] + sy[rows])
+        if not g_top:
+            nxt[G - 1, 1:-1] = tf * (sx[1:-1] + sy[G - 1])
+        if not g_bot:
+            nxt[ny + G, 1:-1] = tf * (sx[1:-1] + sy[ny + G])
+        cur = nxt
+    out = u.copy()
+    j0, j1 = slab.owned_rows()
+    out[j0:j1] = cur[j0:j1]
+    # corners of the global field are never written (BoundaryKernel.hpp:63-84)
+    if not g_top:
+        out[G - 1, 0], out[G - 1, -1] = u[G - 1, 0], u[G - 1, -1]
+    if not g_bot:
+        out[ny + G, 0], out[ny + G, -1] = u[ny + G, 0], u[ny + G, -1]
+    return out
+
+
+def _slab_worker(rank, world, port, NY, NX, steps, ghost, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dx, dy, dt = ol.heat_params(NY, NX)
+        u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=77).reshape(NY + 2, NX + 2)
+        slab = decomp.slab_for(rank, world, NY, NX, ghost)
+        u = slab.window(u0)
+        done = 0
+        for levels in decomp.launch_schedule(steps, ghost, min_depth=2):
+            u = numpy_slab_launch(u, slab, done + 1, levels, dx, dy, dt)
+            done += levels
+            reqs, recvs = [], []
+            for side, other in (("top", "bottom"), ("bottom", "top")):
+                nb = slab.neighbours[side]
+                if nb is None:
+                    continue
+                reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(u[slab.send_rows(side)])), dst=nb, tag=0 if side == "top" else 1))
+                buf = torch.empty(u[slab.recv_rows(side)].shape, dtype=torch.float64)
+                reqs.append(dist.irecv(buf, src=nb, tag=0 if other == "top" else 1))
+                recvs.append((slab.recv_rows(side), buf))
+            for r in reqs:
+                r.wait()
+            for rows, buf in recvs:
+                u[rows] = buf.numpy()
+        np.save(os.path.join(out_dir, f"slab{rank}.npy"), u)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_numpy_slab_launch_is_the_oracle_on_an_undecomposed_field():
+    NY, NX, steps, ghost = 24, 40, 11, 3
+    dx, dy, dt = ol.heat_params(NY, NX)
+    u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=78).reshape(NY + 2, NX + 2)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    slab = decomp.slab_for(0, 1, NY, NX, ghost)
+    u, done = slab.window(u0), 0
+    for levels in decomp.launch_schedule(steps, ghost, min_depth=2):
+        u = numpy_slab_launch(u, slab, done + 1, levels, dx, dy, dt)
+        done += levels
+    out = np.full_like(want, np.nan)
+    slab.stitch(out, u)
+    assert out.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("world,ghost,steps", [(2, 3, 11), (4, 2, 8), (2, 4, 13)])
+def test_slab_decomposed_heat_over_gloo(tmp_path, world, ghost, steps):
+    """Row slabs with ghost rows `ghost` deep, several time levels per exchange, launches of mixed depth: the stitched
+    result equals the undecomposed oracle bit for bit (host-side geometry and exchange logic of multi.HeatSlab)."""
+    NY, NX = 16 * world, 40
+    port = free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_slab_worker, args=(r, world, port, NY, NX, steps, ghost, str(tmp_path))) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0, "a gloo worker failed"
+    dx, dy, dt = ol.heat_params(NY, NX)
+    u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=77).reshape(NY + 2, NX + 2)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    out = np.full((NY + 2, NX + 2), np.nan)
+    for r in range(world):
+        decomp.slab_for(r, world, NY, NX, ghost).stitch(out, np.load(tmp_path / f"slab{r}.npy"))
+    assert out.tobytes() == want.tobytes()
