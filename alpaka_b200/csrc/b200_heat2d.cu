@@ -174,6 +174,55 @@ namespace
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
     }
 
+
+    // ---- the flag protocol of the fused halo exchange, shared by the three kernel families ---------------------------
+    // waitForNeighbours: called by ONE thread of a CTA that is about to read ghost cells. The ghosts hold the neighbours'
+    // border cells of the previous launch once their flag words say so (which also means the neighbours are done READING
+    // the ghost cells this launch overwrites in their other buffer). Bounded spin (about 2 s): a peer that died must not
+    // hang this GPU. Ends with the proxy fence TMA needs: ghosts are written through the generic proxy (peer stores),
+    // the TMA unit reads them through the async proxy.
+    template<int SIDES>
+    __device__ __forceinline__ void waitForNeighbours(double* const (&peerDst)[SIDES], uint32_t const* myFlags, uint32_t step, uint32_t* status)
+    {
+        for(int side = 0; side < SIDES; ++side)
+        {
+            if(peerDst[side] == nullptr)
+                continue;
+            uint32_t seen = 0, spins = 0;
+            for(;;)
+            {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(myFlags + side) : "memory");
+                if(seen + 1u >= step) // seen >= step - 1 without underflow
+                    break;
+                if(++spins > 2000000u)
+                {
+                    atomicExch(status, 1u + uint32_t(side));
+                    break;
+                }
+                __nanosleep(1000);
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+
+    // publishWhenLastStrip: called by ONE thread of a strip CTA after a CTA-wide barrier (every thread has issued the
+    // tile's peer stores). Counts the tile; whoever finishes the LAST strip tile of the launch publishes `step` in the
+    // neighbours' flag words.
+    template<int SIDES>
+    __device__ __forceinline__ void publishWhenLastStrip(uint32_t* stripCounter, uint32_t stripTiles, uint32_t* const (&peerFlag)[SIDES], uint32_t step)
+    {
+        __threadfence_system();
+        uint32_t const done = atomicAdd(stripCounter, 1u);
+        if(done == stripTiles - 1u)
+        {
+            __threadfence_system();
+            *stripCounter = 0u; // ready for the next launch
+            for(int side = 0; side < SIDES; ++side)
+                if(peerFlag[side] != nullptr)
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peerFlag[side]), "r"(step) : "memory");
+        }
+    }
+
     template<int HINT, int RPT>
     __global__ void __launch_bounds__(consumerThreads(RPT) + 32) heatStepKernel(const __grid_constant__ CUtensorMap mapSrc, HeatArgs const A)
     {
@@ -209,34 +258,9 @@ namespace
                 mbarInit(&empty[s], kConsumerWarps);
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // Only strip tiles read ghost cells, and they come first in the tile order: CTAs without a strip tile skip the wait
             if(A.myFlags != nullptr && blockIdx.x < A.stripTiles)
-            {
-                // Only strip tiles read ghost cells, and they come first in the tile order: CTAs without a strip
-                // tile skip the wait. The ghost cells this launch reads hold the neighbours' border cells of time level step-1 once their
-                // flags say so. Bounded spin (about 2 s): a peer that died must not hang this GPU.
-                for(int side = 0; side < 4; ++side)
-                {
-                    if(A.peerDst[side] == nullptr)
-                        continue;
-                    uint32_t seen = 0;
-                    uint32_t spins = 0;
-                    for(;;)
-                    {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
-                        if(seen + 1u >= A.step + 0u) // seen >= step - 1 without underflow at step 0
-                            break;
-                        if(++spins > 2000000u)
-                        {
-                            atomicExch(A.status, 1u + uint32_t(side));
-                            break;
-                        }
-                        __nanosleep(1000);
-                    }
-                }
-                // the ghosts were written through the generic proxy (peer stores); the TMA unit reads them through the
-                // async proxy
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
         }
         __syncthreads();
 
@@ -387,22 +411,10 @@ namespace
                 // finishes the LAST strip tile of the launch publish the time level to the neighbours
                 asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
                 if(tid == 0)
-                {
-                    __threadfence_system();
-                    uint32_t const done = atomicAdd(A.stripCounter, 1u);
-                    if(done == A.stripTiles - 1u)
-                    {
-                        __threadfence_system();
-                        *A.stripCounter = 0u; // ready for the next launch
-                        for(int side = 0; side < 4; ++side)
-                            if(A.peerFlag[side] != nullptr)
-                                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
-                    }
-                }
+                    publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
             }
         }
     }
-
 
     // ------------------------------------------------------------------------------------------------------------
     // TWO time levels per launch (temporal blocking). A stand-alone field is HBM-bound at one read + one write per cell
@@ -624,32 +636,9 @@ namespace
         {
             mbarInit(&full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // strip tiles read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
             if(strip && A.myFlags != nullptr)
-            {
-                // Strip tiles read ghost rows: they hold the neighbours' border rows of the previous launch's time level
-                // once the neighbours' flags say so (which also means the neighbours are done READING the ghost rows
-                // this launch will overwrite in their other buffer). Bounded spin (about 2 s).
-                for(int side = 0; side < 2; ++side)
-                {
-                    if(A.peerDst[side] == nullptr)
-                        continue;
-                    uint32_t seen = 0, spins = 0;
-                    for(;;)
-                    {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
-                        if(seen + 1u >= A.step)
-                            break;
-                        if(++spins > 2000000u)
-                        {
-                            atomicExch(A.status, 1u + uint32_t(side));
-                            break;
-                        }
-                        __nanosleep(1000);
-                    }
-                }
-                // ghosts were written through the generic proxy (peer stores); TMA reads through the async proxy
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
             mbarExpectTx(&full, Step2Geom<TYT>::kBoxBytes);
             tmaLoad2d(smem, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 2, &full);
         }
@@ -673,18 +662,7 @@ namespace
             // of the launch publishes the launch index to the neighbours
             __syncthreads();
             if(tid == 0)
-            {
-                __threadfence_system();
-                uint32_t const done = atomicAdd(A.stripCounter, 1u);
-                if(done == A.stripTiles - 1u)
-                {
-                    __threadfence_system();
-                    *A.stripCounter = 0u;
-                    for(int side = 0; side < 2; ++side)
-                        if(A.peerFlag[side] != nullptr)
-                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
-                }
-            }
+                publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
         }
     }
 
@@ -902,30 +880,9 @@ namespace
         {
             mbarInit(&full, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // strip tiles read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
             if(strip && A.myFlags != nullptr)
-            {
-                // as in heatStep2Kernel: the ghost rows this strip tile reads have arrived (and the neighbours are done
-                // reading the ones this launch overwrites) once their flags show the previous launch
-                for(int side = 0; side < 2; ++side)
-                {
-                    if(A.peerDst[side] == nullptr)
-                        continue;
-                    uint32_t seen = 0, spins = 0;
-                    for(;;)
-                    {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(A.myFlags + side) : "memory");
-                        if(seen + 1u >= A.step)
-                            break;
-                        if(++spins > 2000000u)
-                        {
-                            atomicExch(A.status, 1u + uint32_t(side));
-                            break;
-                        }
-                        __nanosleep(1000);
-                    }
-                }
-                asm volatile("fence.proxy.async;" ::: "memory");
-            }
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
             mbarExpectTx(&full, kBoxBytes);
             tmaLoad2d(smem, &mapSrc, x0 - G::M - 2, y0 - S, &full);
         }
@@ -948,18 +905,7 @@ namespace
         {
             __syncthreads();
             if(tid == 0)
-            {
-                __threadfence_system();
-                uint32_t const done = atomicAdd(A.stripCounter, 1u);
-                if(done == A.stripTiles - 1u)
-                {
-                    __threadfence_system();
-                    *A.stripCounter = 0u;
-                    for(int side = 0; side < 2; ++side)
-                        if(A.peerFlag[side] != nullptr)
-                            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
-                }
-            }
+                publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
         }
     }
 
