@@ -12,6 +12,8 @@
 //   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
 //   --mode=fused3     per THREE steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
 //                     a remainder runs in shallower launches); same bits
+//   --mode=slabs      --slabs=K row slabs of the field in this process, slab k on device k % (number of devices), --levels=G
+//                     (2..4) time levels per launch and per ghost-row exchange (alpaka::b200::Heat2DSlabs); same bits
 //   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
 //   --output=<file>   dump the final (ny+2) x (nx+2) field, unpadded, for the parity tests
 #include "../common/cli.hpp"
@@ -150,6 +152,30 @@ auto main(int argc, char** argv) -> int
             alpaka::wait(computeQueue);
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);
+        }
+        else if(mode == "slabs")
+        {
+            auto const K = static_cast<unsigned>(args.u64("slabs", 2));
+            auto const nDev = static_cast<unsigned>(alpaka::getDevCount(alpaka::Platform<Acc>{}));
+            std::vector<alpaka::DevB200> devs;
+            for(unsigned k = 0; k < K; ++k)
+                devs.push_back(alpaka::getDevByIdx(alpaka::Platform<Acc>{}, k % nDev));
+            alpaka::b200::Heat2DSlabs slabs(devs, ny, nx, dx, dy, dt, static_cast<int>(args.u64("levels", 3)));
+            slabs.upload(uBufHost.data());
+            auto const ts = std::chrono::high_resolution_clock::now();
+            slabs.steps(numTimeSteps);
+            slabs.waitAll();
+            double const secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - ts).count();
+            slabs.download(uBufHost.data()); // owned rows of every slab; the corners keep their initial values
+            auto const [okSlabs, errSlabs] = validateSolution(uBufHost, extent, dx, dy, tMax);
+            if(args.has("output"))
+                cli::writeFile(args.str("output"), uBufHost.data(), sizeof(double) * std::size_t(extent[0]) * extent[1]);
+            std::cout << "{\"driver\": \"heat2d_b200\", \"mode\": \"slabs\", \"slabs\": " << K << ", \"devices\": " << (K < nDev ? K : nDev)
+                      << ", \"ny\": " << ny << ", \"nx\": " << nx << ", \"steps\": " << numTimeSteps << ", \"launches\": " << slabs.launches()
+                      << ", \"seconds\": " << secs << ", \"ms_per_step\": " << secs * 1e3 / numTimeSteps
+                      << ", \"gbs\": " << 16.0 * double(ny) * double(nx) * numTimeSteps * 1e-9 / secs << ", \"max_error\": " << errSlabs << "}" << std::endl;
+            std::cout << (okSlabs ? "Execution results correct!" : "Execution results incorrect!") << std::endl;
+            return okSlabs ? EXIT_SUCCESS : EXIT_FAILURE;
         }
         else
         {

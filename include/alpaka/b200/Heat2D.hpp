@@ -11,6 +11,9 @@
 #include "Kernel.hpp"
 
 #include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace alpaka::b200
@@ -147,5 +150,217 @@ namespace alpaka::b200
         double m_dt, m_rX, m_rY;
         int m_cur = 0;
         std::uint32_t m_step = 0;
+    };
+
+    //! K row slabs of ONE heat field driven from one host thread: slab k lives on devs[k] (devices may repeat -- several
+    //! slabs on one device, which is how the parity tests run on a single GPU). Every launch advances up to `levels`
+    //! (2..4) time levels and exchanges `levels` ghost rows per side straight from the kernel into the neighbour's
+    //! array (peer stores + flag words: b200_heat2d_slab_plan_create / b200_heat2d_step2_halo_f64 /
+    //! b200_heat2d_stepn_halo_f64). The multi-process form of the same thing is alpaka_b200.multi.HeatSlab.
+    //! Host fields are (NY+2) x (NX+2) doubles, rows unpadded, as the reference driver's host buffer.
+    class Heat2DSlabs
+    {
+    public:
+        using Idx = std::uint32_t;
+        using Buf2 = BufB200<double, DimInt<2u>, Idx>;
+        using BufFlags = BufB200<std::uint32_t, DimInt<1u>, Idx>;
+        using Queue = QueueB200<NonBlocking>;
+
+        Heat2DSlabs(std::vector<DevB200> const& devs, Idx NY, Idx NX, double dx, double dy, double dt, int levels = 3)
+            : m_NY(NY)
+            , m_NX(NX)
+            , m_G(static_cast<Idx>(levels))
+            , m_dt(dt)
+            , m_rX(dt / (dx * dx))
+            , m_rY(dt / (dy * dy))
+        {
+            auto const K = static_cast<Idx>(devs.size());
+            if(K == 0 || levels < 2 || levels > 4 || NY % K != 0 || NY / K < 2 * m_G)
+                throw std::runtime_error("Heat2DSlabs: NY must divide into slabs of at least 2*levels rows, levels in 2..4");
+            m_ny = NY / K;
+            bool distinct = false;
+            for(auto const& d : devs)
+                distinct = distinct || d.getNativeHandle() != devs[0].getNativeHandle();
+            if(distinct)
+            {
+                int pairs = 0;
+                check(b200_enable_peer_all(&pairs));
+            }
+            constexpr double pi = math::constants::pi;
+            std::vector<double> sx(NX + 2u);
+            for(Idx i = 0; i < NX + 2u; ++i)
+                sx[i] = std::sin(pi * (static_cast<double>(i) * dx));
+            m_slabs.reserve(K);
+            for(Idx k = 0; k < K; ++k)
+            {
+                Vec<DimInt<2u>, Idx> const ext{m_ny + 2u * m_G, NX + 2u};
+                Slab sl{devs[k], Queue{devs[k]}, allocBuf<double, Idx>(devs[k], ext), allocBuf<double, Idx>(devs[k], ext),
+                        allocBuf<std::uint32_t, Idx>(devs[k], Vec<DimInt<1u>, Idx>{16u}), nullptr,
+                        static_cast<std::int64_t>(k) * m_ny - (static_cast<std::int64_t>(m_G) - 1)};
+                alpaka::memset(sl.queue, sl.flags, 0);
+                alpaka::memset(sl.queue, sl.u[0], 0);
+                alpaka::memset(sl.queue, sl.u[1], 0);
+                std::vector<double> sy(ext[0]);
+                for(Idx j = 0; j < ext[0]; ++j)
+                    sy[j] = std::sin(pi * (static_cast<double>(sl.g0 + static_cast<std::int64_t>(j)) * dy));
+                int const edges = B200_EDGE_LEFT | B200_EDGE_RIGHT | (k == 0 ? B200_EDGE_TOP : 0) | (k == K - 1 ? B200_EDGE_BOTTOM : 0);
+                check(b200_heat2d_slab_plan_create(
+                    devs[k].getNativeHandle(),
+                    std::data(sl.u[0]),
+                    std::data(sl.u[1]),
+                    static_cast<std::size_t>(getPitchesInBytes(sl.u[0])[0]),
+                    m_ny,
+                    NX,
+                    sx.data(),
+                    sy.data(),
+                    edges,
+                    m_G,
+                    &sl.plan));
+                m_slabs.push_back(std::move(sl));
+            }
+            for(Idx k = 0; k < K; ++k)
+            {
+                b200_heat2d_halo halo{};
+                if(k > 0)
+                {
+                    halo.peer_u[0][0] = std::data(m_slabs[k - 1].u[0]);
+                    halo.peer_u[0][1] = std::data(m_slabs[k - 1].u[1]);
+                    halo.peer_flag[0] = std::data(m_slabs[k - 1].flags) + 1; // its slot for ITS bottom side
+                }
+                if(k + 1 < K)
+                {
+                    halo.peer_u[1][0] = std::data(m_slabs[k + 1].u[0]);
+                    halo.peer_u[1][1] = std::data(m_slabs[k + 1].u[1]);
+                    halo.peer_flag[1] = std::data(m_slabs[k + 1].flags) + 0; // its slot for ITS top side
+                }
+                halo.my_flags = std::data(m_slabs[k].flags);
+                wait(m_slabs[k].queue);
+                check(b200_heat2d_plan_set_halo(m_slabs[k].plan, &halo));
+            }
+        }
+        Heat2DSlabs(Heat2DSlabs const&) = delete;
+        auto operator=(Heat2DSlabs const&) -> Heat2DSlabs& = delete;
+        ~Heat2DSlabs()
+        {
+            for(auto& sl : m_slabs)
+                checkNoexcept(b200_heat2d_plan_destroy(sl.plan));
+        }
+
+        //! both ping-pong arrays of every slab start from its window of the field (ghost rows included)
+        void upload(double const* hostField)
+        {
+            for(auto& sl : m_slabs)
+                for(int b = 0; b < 2; ++b)
+                    copyRows(sl, b, 0, m_ny + 2u * m_G, const_cast<double*>(hostField), B200_COPY_H2D);
+            waitAll();
+            m_cur = 0;
+        }
+
+        //! `n` steps: launches of `levels` time levels, a remainder in shallower ones (never a single level: n != 1)
+        void steps(std::uint32_t n)
+        {
+            if(n == 1 || (m_G == 2 && n % 2 != 0))
+                throw std::runtime_error("Heat2DSlabs::steps: a slab cannot advance a single time level");
+            constexpr double pi = math::constants::pi;
+            while(n > 0)
+            {
+                auto k = m_G < n ? m_G : n;
+                if(n - k == 1)
+                    --k;
+                double tf[4] = {};
+                for(Idx l = 0; l < k; ++l)
+                    tf[l] = std::exp(-pi * pi * ((m_step + 1u + l) * m_dt));
+                ++m_launch;
+                for(auto& sl : m_slabs)
+                {
+                    if(k == 2)
+                        check(b200_heat2d_step2_halo_f64(sl.plan, sl.queue.getNativeHandle(), m_cur, m_rX, m_rY, tf[0], tf[1], m_launch));
+                    else
+                        check(b200_heat2d_stepn_halo_f64(sl.plan, sl.queue.getNativeHandle(), m_cur, m_rX, m_rY, static_cast<int>(k), tf, m_launch));
+                    sl.queue.afterEnqueue();
+                }
+                m_step += k;
+                m_cur ^= 1;
+                n -= k;
+            }
+        }
+
+        //! the rows every slab OWNS (core rows, plus the physical ring row on the first / last slab) into the host field
+        void download(double* hostField)
+        {
+            waitAll();
+            for(std::size_t k = 0; k < m_slabs.size(); ++k)
+            {
+                Idx const j0 = k == 0 ? m_G - 1u : m_G;
+                Idx const j1 = k + 1 == m_slabs.size() ? m_ny + m_G + 1u : m_ny + m_G;
+                copyRows(m_slabs[k], m_cur, j0, j1, hostField, B200_COPY_D2H);
+            }
+            waitAll();
+            for(auto& sl : m_slabs)
+            {
+                std::uint32_t status = 0;
+                check(b200_heat2d_halo_status(sl.plan, &status));
+                if(status != 0)
+                    throw std::runtime_error("Heat2DSlabs: a neighbour's flag never arrived (side " + std::to_string(status - 1) + ")");
+            }
+        }
+
+        void waitAll()
+        {
+            for(auto& sl : m_slabs)
+                wait(sl.queue);
+        }
+
+        [[nodiscard]] auto stepsDone() const -> std::uint32_t
+        {
+            return m_step;
+        }
+        [[nodiscard]] auto launches() const -> std::uint32_t
+        {
+            return m_launch;
+        }
+
+    private:
+        struct Slab
+        {
+            DevB200 dev;
+            Queue queue;
+            Buf2 u[2];
+            BufFlags flags;
+            b200_heat2d_plan_t plan;
+            std::int64_t g0; // global padded row of local row 0
+        };
+
+        //! local rows [j0, j1) of array `b` <-> the same global rows of the host field, clipped to the field
+        void copyRows(Slab& sl, int b, Idx j0, Idx j1, double* hostField, int kind)
+        {
+            std::int64_t lo = sl.g0 + j0, hi = sl.g0 + j1;
+            lo = lo < 0 ? 0 : lo;
+            hi = hi > static_cast<std::int64_t>(m_NY) + 2 ? static_cast<std::int64_t>(m_NY) + 2 : hi;
+            if(lo >= hi)
+                return;
+            auto const pitch = static_cast<std::size_t>(getPitchesInBytes(sl.u[b])[0]);
+            auto* const devPtr = reinterpret_cast<char*>(std::data(sl.u[b])) + static_cast<std::size_t>(lo - sl.g0) * pitch;
+            double* const hostPtr = hostField + static_cast<std::size_t>(lo) * (m_NX + 2u);
+            std::size_t const rowBytes = (static_cast<std::size_t>(m_NX) + 2u) * sizeof(double);
+            void* const dst = kind == B200_COPY_H2D ? static_cast<void*>(devPtr) : static_cast<void*>(hostPtr);
+            void const* const src = kind == B200_COPY_H2D ? static_cast<void const*>(hostPtr) : static_cast<void const*>(devPtr);
+            check(b200_memcpy2d_async(
+                sl.dev.getNativeHandle(),
+                dst,
+                kind == B200_COPY_H2D ? pitch : rowBytes,
+                src,
+                kind == B200_COPY_H2D ? rowBytes : pitch,
+                rowBytes,
+                static_cast<std::size_t>(hi - lo),
+                kind,
+                sl.queue.getNativeHandle()));
+        }
+
+        Idx m_NY, m_NX, m_G, m_ny = 0;
+        double m_dt, m_rX, m_rY;
+        std::vector<Slab> m_slabs;
+        int m_cur = 0;
+        std::uint32_t m_step = 0, m_launch = 0;
     };
 } // namespace alpaka::b200

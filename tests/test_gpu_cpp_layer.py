@@ -213,6 +213,26 @@ def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
         assert float(np.max(np.abs(got - want))) <= 1e-12
 
 
+@pytest.mark.parametrize("levels", [2, 3, 4])
+@pytest.mark.parametrize("slabs,shape", [(3, (96, 160)), (2, (256, 700)), (1, (64, 64))])
+def test_heat2d_cpp_slabs_vs_oracle(tmp_path, slabs, shape, levels):
+    """alpaka::b200::Heat2DSlabs: K row slabs in one process (here all on device 0), `levels` time levels per launch and per
+    ghost-row exchange; 62 steps end with shallower launches. Bit-exact against the undecomposed oracle."""
+    ny, nx = shape
+    steps = 62
+    dx, dy, dt = ol.heat_params(ny, nx)
+    out = tmp_path / "u.bin"
+    r = run("heat2d_b200", f"--ny={ny}", f"--nx={nx}", f"--steps={steps}", f"--dt={dt!r}", "--mode=slabs", f"--slabs={slabs}",
+            f"--levels={levels}", f"--output={out}", check=False)
+    assert os.path.exists(out), r.stdout + r.stderr
+    got = np.fromfile(out, dtype=np.float64).reshape(ny + 2, nx + 2)
+    u0 = np.empty((ny + 2, nx + 2))
+    ol.oracle().orc_heat2d_init(P(u0), ny, nx, nx + 2, dx, dy)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    assert got.tobytes() == want.tobytes()
+    assert last_json(r.stdout)["launches"] == len(__import__("alpaka_b200").decomp.launch_schedule(steps, levels, 2))
+
+
 def test_heat2d_reference_configuration_with_run_time_sizes():
     """The shipped configuration (64x64, 4000 steps, tMax 0.1) through the parameterised driver, both modes."""
     for mode in ("functors", "fused", "fused2", "fused3"):
