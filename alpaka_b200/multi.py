@@ -18,35 +18,28 @@ from .decomp import OPPOSITE, SIDES, Tile
 from .runtime import Buf, Queue, memcpy
 
 
-class HeatTile:
-    """One rank's tile of the decomposed field: ping-pong buffers + flag words (both IPC-exportable), the plan, and the
-    step loop. Usage: construct on every rank, exchange `export()` (or `local_pointers()` inside one process), call
-    `connect()`, `upload()` the tile's window of the initial field, then `step(n)`."""
+class _HaloWiring:
+    """What HeatTile and HeatSlab share: exporting / mapping the two field buffers and the flag words, and handing the
+    neighbours' pointers to the plan (b200_heat2d_plan_set_halo). Subclasses provide `tile` (geometry with `neighbours`,
+    `shape`, `rank`), `flags`, `dev`, `_field_bufs()` and `_plan_handle()`."""
 
-    def __init__(self, queue: Queue, tile: Tile, NY: int, NX: int, dt: Optional[float] = None):
-        self.queue, self.dev, self.tile = queue, queue.dev, tile
-        self.NY, self.NX = NY, NX
-        self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)  # heatEquation2D.cpp:62-63 on the GLOBAL grid
-        self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
-        self.h = heat2d.Heat2D(queue, tile.ny, tile.nx, self.dx, self.dy, self.dt, edges=tile.edges,
-                               j_offset=tile.j_offset, i_offset=tile.i_offset, ipc=True)
-        self.flags = Buf(self.dev, np.uint32, 16, ipc=True)
-        lib = _lib.load()
-        check(lib.b200_memset_async(self.dev.idx, self.flags.ptr, 0, 64, queue.handle))
-        queue.wait()
-        self._opened: list[int] = []
-        self.connected = False
+    def _field_bufs(self):
+        raise NotImplementedError
 
-    # ---- wiring
+    def _plan_handle(self):
+        raise NotImplementedError
+
     def local_pointers(self) -> dict:
-        return {"u0": self.h.bufs[0].ptr, "u1": self.h.bufs[1].ptr, "flags": self.flags.ptr, "dev": self.dev.idx,
-                "shape": self.tile.shape, "pitch": self.h.bufs[0].pitch_bytes}
+        u0, u1 = self._field_bufs()
+        return {"u0": u0.ptr, "u1": u1.ptr, "flags": self.flags.ptr, "dev": self.dev.idx, "shape": self.tile.shape,
+                "pitch": u0.pitch_bytes}
 
     def export(self) -> dict:
         """CUDA-IPC handles of the two field buffers and the flag words (picklable)."""
         lib = _lib.load()
-        out = {"shape": self.tile.shape, "pitch": self.h.bufs[0].pitch_bytes, "rank": self.tile.rank}
-        for name, ptr in (("u0", self.h.bufs[0].ptr), ("u1", self.h.bufs[1].ptr), ("flags", self.flags.ptr)):
+        u0, u1 = self._field_bufs()
+        out = {"shape": self.tile.shape, "pitch": u0.pitch_bytes, "rank": self.tile.rank}
+        for name, ptr in (("u0", u0.ptr), ("u1", u1.ptr), ("flags", self.flags.ptr)):
             hb = C.create_string_buffer(64)
             check(lib.b200_ipc_get_mem_handle(self.dev.idx, ptr, hb))
             out[name] = hb.raw
@@ -66,20 +59,59 @@ class HeatTile:
     def connect(self, peers: dict) -> None:
         """peers: side -> pointers dict of the neighbour on that side (None / missing on physical boundaries)."""
         halo = Heat2dHalo()
+        pitch = self._field_bufs()[0].pitch_bytes
         for k, side in enumerate(SIDES):
             nb = peers.get(side)
             if (nb is None) != (self.tile.neighbours[side] is None):
                 raise B200Error(-1, f"heat tile {self.tile.rank}: neighbour on side '{side}' does not match the decomposition")
             if nb is None:
                 continue
-            if tuple(nb["shape"]) != self.tile.shape or nb["pitch"] != self.h.bufs[0].pitch_bytes:
+            if tuple(nb["shape"]) != tuple(self.tile.shape) or nb["pitch"] != pitch:
                 raise B200Error(-1, "heat tiles must have identical extents and pitches")
             halo.peer_u[k][0] = nb["u0"]
             halo.peer_u[k][1] = nb["u1"]
             halo.peer_flag[k] = nb["flags"] + 4 * SIDES.index(OPPOSITE[side])
         halo.my_flags = self.flags.ptr
-        check(_lib.load().b200_heat2d_plan_set_halo(self.h.plan, C.byref(halo)))
+        check(_lib.load().b200_heat2d_plan_set_halo(self._plan_handle(), C.byref(halo)))
         self.connected = True
+
+    def status(self) -> int:
+        """0, or 1 + side of the first flag wait that timed out."""
+        s = C.c_uint32(0)
+        check(_lib.load().b200_heat2d_halo_status(self._plan_handle(), C.byref(s)))
+        return int(s.value)
+
+    def _close_peers(self) -> None:
+        lib = _lib.load()
+        for p in self._opened:
+            lib.b200_ipc_close_mem_handle(self.dev.idx, p)
+        self._opened = []
+
+
+class HeatTile(_HaloWiring):
+    """One rank's tile of the decomposed field: ping-pong buffers + flag words (both IPC-exportable), the plan, and the
+    step loop. Usage: construct on every rank, exchange `export()` (or `local_pointers()` inside one process), call
+    `connect()`, `upload()` the tile's window of the initial field, then `step(n)`."""
+
+    def __init__(self, queue: Queue, tile: Tile, NY: int, NX: int, dt: Optional[float] = None):
+        self.queue, self.dev, self.tile = queue, queue.dev, tile
+        self.NY, self.NX = NY, NX
+        self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)  # heatEquation2D.cpp:62-63 on the GLOBAL grid
+        self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
+        self.h = heat2d.Heat2D(queue, tile.ny, tile.nx, self.dx, self.dy, self.dt, edges=tile.edges,
+                               j_offset=tile.j_offset, i_offset=tile.i_offset, ipc=True)
+        self.flags = Buf(self.dev, np.uint32, 16, ipc=True)
+        lib = _lib.load()
+        check(lib.b200_memset_async(self.dev.idx, self.flags.ptr, 0, 64, queue.handle))
+        queue.wait()
+        self._opened: list[int] = []
+        self.connected = False
+
+    def _field_bufs(self):
+        return self.h.bufs
+
+    def _plan_handle(self):
+        return self.h.plan
 
     # ---- data
     def upload(self, local_field: np.ndarray) -> None:
@@ -104,24 +136,16 @@ class HeatTile:
             h.cur ^= 1
         self.queue._after_enqueue()
 
-    def status(self) -> int:
-        s = C.c_uint32(0)
-        check(_lib.load().b200_heat2d_halo_status(self.h.plan, C.byref(s)))
-        return int(s.value)
-
     def download(self) -> np.ndarray:
         return self.h.download()
 
     def close(self) -> None:
-        lib = _lib.load()
-        for p in self._opened:
-            lib.b200_ipc_close_mem_handle(self.dev.idx, p)
-        self._opened = []
+        self._close_peers()
         self.h.close()
         self.flags.free()
 
 
-class HeatSlab(HeatTile):
+class HeatSlab(_HaloWiring):
     """One rank's ROW SLAB of the field, advanced `levels` (2, 3 or 4) time levels per launch and per exchange
     (b200_heat2d_slab_plan_create + b200_heat2d_step2_halo_f64 / b200_heat2d_stepn_halo_f64, include/b200/b200.h): the
     temporal blocking of the stand-alone kernels carried to several GPUs. Ghost rows are G = `levels` deep, so the
@@ -167,7 +191,12 @@ class HeatSlab(HeatTile):
         queue.wait()
         self._opened = []
         self.connected = False
-        self.h = self  # HeatTile's wiring code reads h.bufs / h.plan
+
+    def _field_bufs(self):
+        return self.bufs
+
+    def _plan_handle(self):
+        return self.plan
 
     # ---- data
     def window(self, global_field: np.ndarray) -> np.ndarray:
@@ -215,11 +244,6 @@ class HeatSlab(HeatTile):
             self.cur ^= 1
         self.queue._after_enqueue()
 
-    def status(self) -> int:
-        s = C.c_uint32(0)
-        check(_lib.load().b200_heat2d_halo_status(self.plan, C.byref(s)))
-        return int(s.value)
-
     def download(self) -> np.ndarray:
         out = np.empty(self.tile.shape, dtype=np.float64)
         self.queue.wait()
@@ -236,20 +260,14 @@ class HeatSlab(HeatTile):
         self.tile.stitch(global_out, local_field)
 
     def close(self) -> None:
-        lib = _lib.load()
-        for p in self._opened:
-            lib.b200_ipc_close_mem_handle(self.dev.idx, p)
-        self._opened = []
+        self._close_peers()
         if getattr(self, "plan", None):
-            lib.b200_heat2d_plan_destroy(self.plan)
+            _lib.load().b200_heat2d_plan_destroy(self.plan)
             self.plan = None
         for b in self.bufs:
             b.free()
         self.bufs = []
         self.flags.free()
-
-    def __del__(self):
-        pass
 
 
 def connect_over_process_group(tile_runner: HeatTile, dist) -> None:
