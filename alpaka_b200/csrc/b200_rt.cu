@@ -289,6 +289,15 @@ extern "C"
                     (void) cudaGetLastError();
                 else
                     B200_CUDA(e);
+                // cudaDeviceEnablePeerAccess covers cudaMalloc memory only: buffers come from the stream-ordered pool
+                // (b200_malloc_async), whose access is granted per pool. Device i may now read and write device j's pool.
+                cudaMemPool_t pool;
+                B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, j));
+                cudaMemAccessDesc desc{};
+                desc.location.type = cudaMemLocationTypeDevice;
+                desc.location.id = i;
+                desc.flags = cudaMemAccessFlagsProtReadWrite;
+                B200_CUDA(cudaMemPoolSetAccess(pool, &desc, 1));
                 ++enabled;
             }
         }

@@ -72,8 +72,10 @@ extern "C"
     int b200_device_mem_info(int dev, uint64_t* free_bytes, uint64_t* total_bytes);
     int b200_device_sync(int dev); /* trait::CurrentThreadWaitFor<Dev> */
     int b200_device_reset(int dev); /* trait::Reset */
-    /* cudaDeviceEnablePeerAccess all-to-all; the reference never enables it and relies on
-     * UVA staging. n_pairs_enabled may be NULL. */
+    /* cudaDeviceEnablePeerAccess all-to-all, and read/write access of every device to every other device's
+     * stream-ordered pool (cudaMemPoolSetAccess: peer access proper covers cudaMalloc memory only), so that kernels may
+     * load and store through pointers of buffers on other devices. The reference never enables peer access (SURVEY.md
+     * section 2.1) and relies on UVA staging. n_pairs_enabled may be NULL. */
     int b200_enable_peer_all(int* n_pairs_enabled);
 
     /* ---------------------------------------------------------------------------------------------

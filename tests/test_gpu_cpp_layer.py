@@ -233,6 +233,28 @@ def test_heat2d_cpp_slabs_vs_oracle(tmp_path, slabs, shape, levels):
     assert last_json(r.stdout)["launches"] == len(__import__("alpaka_b200").decomp.launch_schedule(steps, levels, 2))
 
 
+def test_heat2d_cpp_slabs_on_several_devices(tmp_path):
+    """The same with one slab per DEVICE of this process (peer stores over NVLink into the other device's pool memory:
+    b200_enable_peer_all grants the pools' access). Needs >= 2 devices."""
+    import alpaka_b200 as ab
+
+    ndev = ab.Platform().get_dev_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 devices")
+    slabs = min(ndev, 4)
+    ny, nx, steps = 128 * slabs, 900, 30
+    dx, dy, dt = ol.heat_params(ny, nx)
+    out = tmp_path / "u.bin"
+    r = run("heat2d_b200", f"--ny={ny}", f"--nx={nx}", f"--steps={steps}", f"--dt={dt!r}", "--mode=slabs", f"--slabs={slabs}",
+            "--levels=3", f"--output={out}", check=False)
+    assert os.path.exists(out), r.stdout + r.stderr
+    assert last_json(r.stdout)["devices"] == slabs
+    got = np.fromfile(out, dtype=np.float64).reshape(ny + 2, nx + 2)
+    u0 = np.empty((ny + 2, nx + 2))
+    ol.oracle().orc_heat2d_init(P(u0), ny, nx, nx + 2, dx, dy)
+    assert got.tobytes() == ol.orc_heat_run(u0, 1, steps, dx, dy, dt).tobytes()
+
+
 def test_heat2d_reference_configuration_with_run_time_sizes():
     """The shipped configuration (64x64, 4000 steps, tMax 0.1) through the parameterised driver, both modes."""
     for mode in ("functors", "fused", "fused2", "fused3"):
