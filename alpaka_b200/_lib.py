@@ -78,6 +78,14 @@ class Heat2dHalo(C.Structure):
     ]
 
 
+class Exchange(C.Structure):
+    """b200_exchange: every rank's exchange buffer as seen from this device (fused Dot / reduce over several GPUs)."""
+
+    _fields_ = [("base", C.c_void_p * 16), ("world", C.c_uint32), ("rank", C.c_uint32)]
+
+
+EXCHANGE_BYTES = 512
+
 _vp, _u64, _u32, _i, _sz = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_size_t
 _f64, _f32 = C.c_double, C.c_float
 _P = C.POINTER
@@ -155,6 +163,12 @@ SIGNATURES: dict[str, list] = {
     "b200_reduce_sum_u64": [_vp, _vp, _u64, _vp, _vp],
     "b200_reduce_sum_f32": [_vp, _vp, _u64, _vp, _vp],
     "b200_reduce_sum_f64": [_vp, _vp, _u64, _vp, _vp],
+    "b200_dot_allranks_f64": [_vp, _vp, _vp, _u64, _vp, _vp, _P(Exchange), _u32],
+    "b200_dot_allranks_f32": [_vp, _vp, _vp, _u64, _vp, _vp, _P(Exchange), _u32],
+    "b200_reduce_sum_allranks_u32": [_vp, _vp, _u64, _vp, _vp, _P(Exchange), _u32],
+    "b200_reduce_sum_allranks_f32": [_vp, _vp, _u64, _vp, _vp, _P(Exchange), _u32],
+    "b200_reduce_sum_allranks_f64": [_vp, _vp, _u64, _vp, _vp, _P(Exchange), _u32],
+    "b200_exchange_status": [_i, _vp, _P(_u32)],
     "b200_heat2d_plan_create": [_i, _vp, _vp, _sz, _u32, _u32, _vp, _vp, _i, _P(_vp)],
     "b200_heat2d_plan_destroy": [_vp],
     "b200_heat2d_step_f64": [_vp, _vp, _i, _f64, _f64, _f64],

@@ -11,6 +11,10 @@
 //   level 2  warp tree with __shfl_down_sync (no barriers), one shared-memory slot per warp, first warp finishes;
 //   level 3  block partial -> scratch[blockIdx]; __threadfence(); atomic ticket; the LAST block to arrive folds the
 //            partials in a fixed order (thread t takes t, t+B, ...; then the same block tree) and writes the scalar.
+//   level 4  (several GPUs, optional) the same last block stores the device's scalar straight into every rank's slot
+//            array through peer pointers (NVLink P2P / CUDA-IPC mappings), publishes the call number in their flag words
+//            (st.release.sys), waits for the other ranks' flags (ld.acquire.sys) and folds the slots in RANK ORDER: the
+//            all-ranks result comes out of the SAME launch on every rank, bit-identical everywhere -- no NCCL, no host.
 // One launch, no host fold, no second kernel. The order of additions depends only on (n, grid, block), which depend
 // only on the device -> bit-reproducible run to run. Products use __dmul_rn + __dadd_rn (no FMA), matching the
 // oracle's pinned contraction; integer sums wrap (order-free, bit-exact vs the reference).
@@ -116,6 +120,76 @@ namespace
         return *reinterpret_cast<T const volatile*>(p);
     }
 
+    // Exchange buffer of ONE rank (B200_EXCHANGE_BYTES, zeroed once): slots[2][kMaxRanks] 8-byte containers (two parities of
+    // the call number), then flags[kMaxRanks] (u32, the call number each rank last published here), then a status word.
+    constexpr int kMaxRanks = B200_EXCHANGE_MAX_RANKS;
+    constexpr size_t kFlagsOffset = 2 * size_t(kMaxRanks) * 8;
+    constexpr size_t kStatusOffset = kFlagsOffset + size_t(kMaxRanks) * 4;
+    static_assert(kStatusOffset + 4 <= B200_EXCHANGE_BYTES);
+
+    struct Exchange
+    {
+        char* base[kMaxRanks]; // base[r]: rank r's exchange buffer as seen from this device; base[rank] is the own one
+        uint32_t world, rank, step; // world <= 1: no exchange
+    };
+
+    // Called by the threads of the last block after thread 0 produced this device's scalar `mine`. Returns (in thread 0)
+    // the sum over all ranks, folded left to right in rank order.
+    template<typename T>
+    __device__ __forceinline__ T exchangeAllRanks(Exchange const& X, T mine, uint64_t* smemSlots)
+    {
+        __shared__ uint64_t mineBits;
+        if(threadIdx.x == 0)
+        {
+            uint64_t u = 0;
+            memcpy(&u, &mine, sizeof(T));
+            mineBits = u;
+        }
+        __syncthreads();
+        uint32_t const parity = X.step & 1u;
+        if(threadIdx.x < X.world)
+        {
+            // thread p: my scalar into rank p's slot for me, then the call number into its flag for me
+            uint32_t const p = threadIdx.x;
+            auto* slot = reinterpret_cast<uint64_t*>(X.base[p]) + parity * kMaxRanks + X.rank;
+            auto* flag = reinterpret_cast<uint32_t*>(X.base[p] + kFlagsOffset) + X.rank;
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(mineBits) : "memory");
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(X.step) : "memory");
+            // ... and rank p's scalar out of MY buffer once its flag says it has arrived (bounded spin, about 2 s)
+            char* const my = X.base[X.rank];
+            auto const* myFlag = reinterpret_cast<uint32_t const*>(my + kFlagsOffset) + p;
+            uint32_t seen = 0, spins = 0;
+            for(;;)
+            {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(myFlag) : "memory");
+                if(seen >= X.step)
+                    break;
+                if(++spins > 2000000u)
+                {
+                    atomicExch(reinterpret_cast<uint32_t*>(my + kStatusOffset), 1u + p);
+                    break;
+                }
+                __nanosleep(1000);
+            }
+            uint64_t v;
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<uint64_t const*>(my) + parity * kMaxRanks + p) : "memory");
+            smemSlots[p] = v;
+        }
+        __syncthreads();
+        T total = T(0);
+        if(threadIdx.x == 0)
+        {
+            memcpy(&total, &smemSlots[0], sizeof(T));
+            for(uint32_t r = 1; r < X.world; ++r)
+            {
+                T v;
+                memcpy(&v, &smemSlots[r], sizeof(T));
+                total = addv(total, v);
+            }
+        }
+        return total;
+    }
+
     // DOT: sum a[i]*b[i]; otherwise sum a[i].
     template<typename T, bool DOT, int UNROLL>
     __global__ void __launch_bounds__(kBlock) reduceKernel(
@@ -126,10 +200,12 @@ namespace
         T* __restrict__ partials,
         unsigned int* __restrict__ ticket,
         T* __restrict__ out,
-        uint32_t const nOut)
+        uint32_t const nOut,
+        Exchange const X)
     {
         constexpr int N = 32 / int(sizeof(T));
         __shared__ T warpSlots[32];
+        __shared__ uint64_t rankSlots[kMaxRanks];
         __shared__ bool isLast;
 
         T acc[UNROLL];
@@ -200,6 +276,8 @@ namespace
                 s = addv(s, ldVolatile(partials + i));
             __syncthreads(); // warpSlots reuse
             s = blockSum(s, warpSlots);
+            if(X.world > 1)
+                s = exchangeAllRanks(X, s, rankSlots); // level 4: all ranks, rank order, same launch
             if(threadIdx.x == 0)
                 out[0] = s;
         }
@@ -219,9 +297,22 @@ namespace
     }
 
     template<typename T, bool DOT>
-    int launchReduce(b200_stream_t stream, T const* a, T const* b, uint64_t n, T* out, uint32_t nOut, void* scratch)
+    int launchReduce(b200_stream_t stream, T const* a, T const* b, uint64_t n, T* out, uint32_t nOut, void* scratch, b200_exchange const* ex = nullptr, uint32_t step = 0)
     {
         B200_REQUIRE(out && scratch && nOut >= 1, B200_EINVAL);
+        Exchange X{};
+        if(ex != nullptr)
+        {
+            B200_REQUIRE(nOut == 1 && step >= 1 && ex->world >= 1 && ex->world <= uint32_t(kMaxRanks) && ex->rank < ex->world, B200_EINVAL);
+            for(uint32_t r = 0; r < ex->world; ++r)
+            {
+                B200_REQUIRE(ex->base[r] != nullptr && reinterpret_cast<uintptr_t>(ex->base[r]) % 8 == 0, B200_EINVAL);
+                X.base[r] = static_cast<char*>(ex->base[r]);
+            }
+            X.world = ex->world;
+            X.rank = ex->rank;
+            X.step = step;
+        }
         B200_REQUIRE(n == 0 || (a && (!DOT || b)), B200_EINVAL);
         B200_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, B200_EALIGN);
         auto const s = reinterpret_cast<cudaStream_t>(stream);
@@ -243,13 +334,13 @@ namespace
         switch(unroll)
         {
         case 1:
-            reduceKernel<T, DOT, 1><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut);
+            reduceKernel<T, DOT, 1><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut, X);
             break;
         case 2:
-            reduceKernel<T, DOT, 2><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut);
+            reduceKernel<T, DOT, 2><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut, X);
             break;
         case 4:
-            reduceKernel<T, DOT, 4><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut);
+            reduceKernel<T, DOT, 4><<<unsigned(grid), kBlock, 0, s>>>(a, b, n, nVec, partials, ticket, out, nOut, X);
             break;
         default:
             return b200::fail(B200_EINVAL, "unroll must be 1, 2 or 4", __FILE__, __LINE__);
@@ -306,5 +397,44 @@ extern "C"
     int b200_reduce_sum_f64(b200_stream_t s, double const* in, uint64_t n, double* out_dev, void* scratch)
     {
         return launchReduce<double, false>(s, in, nullptr, n, out_dev, 1, scratch);
+    }
+
+    // ---- the same reductions with the all-ranks exchange fused into the launch
+    int b200_dot_allranks_f64(b200_stream_t s, double const* a, double const* b, uint64_t n, double* out_dev, void* scratch, b200_exchange const* ex, uint32_t step)
+    {
+        B200_REQUIRE(ex, B200_EINVAL);
+        return launchReduce<double, true>(s, a, b, n, out_dev, 1, scratch, ex, step);
+    }
+
+    int b200_dot_allranks_f32(b200_stream_t s, float const* a, float const* b, uint64_t n, float* out_dev, void* scratch, b200_exchange const* ex, uint32_t step)
+    {
+        B200_REQUIRE(ex, B200_EINVAL);
+        return launchReduce<float, true>(s, a, b, n, out_dev, 1, scratch, ex, step);
+    }
+
+    int b200_reduce_sum_allranks_u32(b200_stream_t s, uint32_t const* in, uint64_t n, uint32_t* out_dev, void* scratch, b200_exchange const* ex, uint32_t step)
+    {
+        B200_REQUIRE(ex, B200_EINVAL);
+        return launchReduce<uint32_t, false>(s, in, nullptr, n, out_dev, 1, scratch, ex, step);
+    }
+
+    int b200_reduce_sum_allranks_f32(b200_stream_t s, float const* in, uint64_t n, float* out_dev, void* scratch, b200_exchange const* ex, uint32_t step)
+    {
+        B200_REQUIRE(ex, B200_EINVAL);
+        return launchReduce<float, false>(s, in, nullptr, n, out_dev, 1, scratch, ex, step);
+    }
+
+    int b200_reduce_sum_allranks_f64(b200_stream_t s, double const* in, uint64_t n, double* out_dev, void* scratch, b200_exchange const* ex, uint32_t step)
+    {
+        B200_REQUIRE(ex, B200_EINVAL);
+        return launchReduce<double, false>(s, in, nullptr, n, out_dev, 1, scratch, ex, step);
+    }
+
+    int b200_exchange_status(int dev, void const* own_exchange_buffer, uint32_t* status)
+    {
+        B200_REQUIRE(own_exchange_buffer && status, B200_EINVAL);
+        B200_CUDA(cudaSetDevice(dev));
+        B200_CUDA(cudaMemcpy(status, static_cast<char const*>(own_exchange_buffer) + kStatusOffset, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        return 0;
     }
 }

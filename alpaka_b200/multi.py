@@ -292,6 +292,119 @@ def connect_in_process(runners: list) -> None:
         r.connect(peers)
 
 
+class ScalarExchange:
+    """One rank's end of the Dot / reduce exchange FUSED into the reduction launch (b200_dot_allranks_* /
+    b200_reduce_sum_allranks_*, include/b200/b200.h): the last block of the single-pass reduction stores this device's
+    scalar into every rank's slot array through peer pointers, publishes the call number, waits for the others and folds
+    the slots in rank order -- the all-ranks value comes out of the same launch, bit-identical on every rank, without NCCL
+    or the host. Usage: construct on every rank, connect_exchange_over_process_group(ex, dist) (or
+    connect_exchange_in_process([...])), then ex.dot(queue, a, b) / ex.reduce_sum(queue, x) collectively."""
+
+    _ALLRANKS = {np.dtype(np.float64): "f64", np.dtype(np.float32): "f32", np.dtype(np.uint32): "u32"}
+
+    def __init__(self, queue: Queue, rank: int, world: int):
+        if not (1 <= world <= 16 and 0 <= rank < world):
+            raise B200Error(-1, "ScalarExchange: between 1 and 16 ranks")
+        self.dev, self.rank, self.world = queue.dev, rank, world
+        self.buf = Buf(self.dev, np.uint8, _lib.EXCHANGE_BYTES, ipc=True)
+        check(_lib.load().b200_memset_async(self.dev.idx, self.buf.ptr, 0, _lib.EXCHANGE_BYTES, queue.handle))
+        queue.wait()
+        self.step = 0
+        self._opened: list[int] = []
+        self.desc = None
+
+    def export(self) -> bytes:
+        hb = C.create_string_buffer(64)
+        check(_lib.load().b200_ipc_get_mem_handle(self.dev.idx, self.buf.ptr, hb))
+        return hb.raw
+
+    def open_peer(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        check(_lib.load().b200_ipc_open_mem_handle(self.dev.idx, handle, C.byref(p)))
+        self._opened.append(p.value)
+        return p.value
+
+    def connect(self, bases: list) -> None:
+        """bases[r]: rank r's exchange buffer as seen from this device (own pointer at index `rank`)."""
+        if len(bases) != self.world or bases[self.rank] != self.buf.ptr:
+            raise B200Error(-1, "ScalarExchange.connect: one pointer per rank, the own buffer at the own rank")
+        d = _lib.Exchange()
+        for r, ptr in enumerate(bases):
+            d.base[r] = ptr
+        d.world, d.rank = self.world, self.rank
+        self.desc = d
+
+    def _call(self, name: str, queue: Queue, *args) -> None:
+        if self.desc is None:
+            raise B200Error(-1, "ScalarExchange used before connect()")
+        self.step += 1
+        check(getattr(_lib.load(), name)(queue.handle, *args, queue.reduce_scratch(), C.byref(self.desc), self.step))
+        queue._after_enqueue()
+
+    def dot_async(self, queue: Queue, a: Buf, b: Buf, out: Buf, n: Optional[int] = None) -> None:
+        """Collective: out[0] (device) = sum over all ranks of sum_i a[i]*b[i] of the rank's slab."""
+        sfx = self._ALLRANKS.get(a.dtype)
+        if sfx not in ("f64", "f32") or b.dtype != a.dtype or out.dtype != a.dtype:
+            raise B200Error(-1, "dot over all ranks: float32 or float64 buffers of one type")
+        n = a.extent[0] if n is None else n
+        self._call(f"b200_dot_allranks_{sfx}", queue, a.ptr, b.ptr, n, out.ptr)
+
+    def reduce_sum_async(self, queue: Queue, source: Buf, out: Buf, n: Optional[int] = None) -> None:
+        sfx = self._ALLRANKS.get(source.dtype)
+        if sfx is None or out.dtype != source.dtype:
+            raise B200Error(-1, "reduce over all ranks: uint32, float32 or float64 buffers of one type")
+        n = source.extent[0] if n is None else n
+        self._call(f"b200_reduce_sum_allranks_{sfx}", queue, source.ptr, n, out.ptr)
+
+    def _to_host(self, queue: Queue, out: Buf):
+        host = np.empty(1, dtype=out.dtype)
+        memcpy(queue, host, out)
+        queue.wait()
+        out.free()
+        return host[0]
+
+    def dot(self, queue: Queue, a: Buf, b: Buf, n: Optional[int] = None):
+        from .runtime import alloc_buf
+
+        out = alloc_buf(queue.dev, a.dtype, 1, queue)
+        self.dot_async(queue, a, b, out, n)
+        return self._to_host(queue, out)
+
+    def reduce_sum(self, queue: Queue, source: Buf, n: Optional[int] = None):
+        from .runtime import alloc_buf
+
+        out = alloc_buf(queue.dev, source.dtype, 1, queue)
+        self.reduce_sum_async(queue, source, out, n)
+        return self._to_host(queue, out)
+
+    def status(self) -> int:
+        s = C.c_uint32(0)
+        check(_lib.load().b200_exchange_status(self.dev.idx, self.buf.ptr, C.byref(s)))
+        return int(s.value)
+
+    def close(self) -> None:
+        lib = _lib.load()
+        for p in self._opened:
+            lib.b200_ipc_close_mem_handle(self.dev.idx, p)
+        self._opened = []
+        self.buf.free()
+
+
+def connect_exchange_over_process_group(ex: ScalarExchange, dist) -> None:
+    """One process per GPU: all-gather the IPC handles once and map every other rank's exchange buffer."""
+    handles = [None] * ex.world
+    dist.all_gather_object(handles, ex.export())
+    ex.connect([ex.buf.ptr if r == ex.rank else ex.open_peer(handles[r]) for r in range(ex.world)])
+    dist.barrier()
+
+
+def connect_exchange_in_process(exchanges: list) -> None:
+    """One process driving all ranks (tests: several ranks on one device; or several peer-enabled devices)."""
+    ptrs = [e.buf.ptr for e in exchanges]
+    for e in exchanges:
+        e.connect(list(ptrs))
+
+
 def dot_all_ranks(local_value: float, dist, device) -> float:
     """Dot's exchange step: one double per rank, gathered (NCCL all_gather of 8 bytes) and summed in rank order."""
     import torch

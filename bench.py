@@ -294,19 +294,22 @@ def run_ours(args):
         record("add_f64", timed(lambda: bs.add(q, a, b, c), Ks, 3), 24.0 * n)
         record("nstream_f64", timed(lambda: bs.nstream(q, c, a, b, 0.0), Ks, 3), 32.0 * n)
         out = ab.alloc_buf(dev, np.float64, 1, q)
-        record("dot_f64", timed(lambda: bs.dot_async(q, a, b, out), Ks, 3), 16.0 * n)
-        dot_local = np.empty(1)
-        ab.memcpy(q, dot_local, out)
-        q.wait()
-        dot_total = float(dot_local[0])
-        if dist is not None:
-            # Dot's exchange step: one scalar per GPU, combined in rank order for bit-stable results
-            import torch
+        exch = None
+        if dist is None:
+            record("dot_f64", timed(lambda: bs.dot_async(q, a, b, out), Ks, 3), 16.0 * n)
+        else:
+            # Dot's exchange step (one scalar per GPU, combined in rank order) is FUSED into the reduction launch: peer
+            # stores + flag words from the last block, no NCCL and no host step inside the timed region
+            from alpaka_b200 import multi as _multi
 
-            mine = torch.tensor([dot_local[0]], dtype=torch.float64, device=f"cuda:{local_rank}")
-            parts = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(parts, mine)
-            dot_total = float(sum(float(p.item()) for p in parts))
+            exch = _multi.ScalarExchange(q, rank, world)
+            _multi.connect_exchange_over_process_group(exch, dist)
+            record("dot_f64", timed(lambda: exch.dot_async(q, a, b, out), Ks, 3), 16.0 * n)
+            kernels["dot_f64"]["exchange"] = "all ranks, fused into the launch (peer stores + flags), rank-ordered"
+        dot_host = np.empty(1)
+        ab.memcpy(q, dot_host, out)
+        q.wait()
+        dot_total = float(dot_host[0])
         assert dot_total == 2.0 * n * world, f"Dot check failed: {dot_total} != {2.0 * n * world}"
         out.free()
 
@@ -322,18 +325,29 @@ def run_ours(args):
         # fill with ones via the f32 init kernel's bit pattern is not exact for u32; memset 0x01010101 instead
         ab.memset(q, src, 1)
         Ks = max(5, K // 2)
-        record("reduce_u32", timed(lambda: ab.reduce.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+        if exch is None:
+            record("reduce_u32", timed(lambda: ab.reduce.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+        else:
+            record("reduce_u32", timed(lambda: exch.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+            kernels["reduce_u32"]["exchange"] = kernels["dot_f64"]["exchange"]
         got = np.empty(1, dtype=np.uint32)
         ab.memcpy(q, got, res)
         q.wait()
-        assert int(got[0]) == (0x01010101 * nr) % 2**32, "reduce u32 check failed"
+        assert int(got[0]) == (0x01010101 * nr * world) % 2**32, "reduce u32 check failed"
         src.free()
         res.free()
         nf = (1 << 30) if not args.n else n
         srcf = ab.alloc_buf(dev, np.float32, nf, q)
         resf = ab.alloc_buf(dev, np.float32, 1, q)
         ab.memset(q, srcf, 0)
-        record("reduce_f32", timed(lambda: ab.reduce.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+        if exch is None:
+            record("reduce_f32", timed(lambda: ab.reduce.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+        else:
+            record("reduce_f32", timed(lambda: exch.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+            kernels["reduce_f32"]["exchange"] = kernels["dot_f64"]["exchange"]
+            assert exch.status() == 0, "a rank's flag never arrived in the fused Dot/reduce exchange"
+            barrier()
+            exch.close()
         for bf in (srcf, resf):
             bf.free()
 

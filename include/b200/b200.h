@@ -260,6 +260,34 @@ extern "C"
     int b200_reduce_sum_f32(b200_stream_t s, float const* in, uint64_t n, float* out_dev, void* scratch);
     int b200_reduce_sum_f64(b200_stream_t s, double const* in, uint64_t n, double* out_dev, void* scratch);
 
+    /* ---- Dot / reduce over SEVERAL GPUs with the exchange step fused into the launch (new; SURVEY.md section 8e: the
+     * slab-sharded Dot and reduce exchange ONE scalar per rank). The last block of the single-pass reduction stores the
+     * device's scalar straight into every rank's slot array through peer pointers (CUDA-IPC mappings, one process per
+     * GPU, or plain pointers after b200_enable_peer_all inside one process), publishes the call number `step` in their
+     * flag words, waits (bounded) for the other ranks' flags and folds the slots left to right in RANK ORDER -- the
+     * combination order does not depend on a collective library, so the result is bit-identical on every rank
+     * (SURVEY.md section 7.3-10). out_dev[0] holds the all-ranks value when the launch completes. No NCCL, no host step.
+     *   base[r]  rank r's exchange buffer (B200_EXCHANGE_BYTES of plain device memory from b200_malloc_device, zeroed
+     *            once) as seen from this device; base[rank] is the own one
+     *   step     1, 2, 3, ... : the same number on every rank for the same collective call
+     * Slots are double-buffered by the parity of `step`, which suffices because a rank cannot finish call k+1 before
+     * every rank has entered it, i.e. has finished reading call k's slots. */
+#define B200_EXCHANGE_MAX_RANKS 16
+#define B200_EXCHANGE_BYTES 512u
+    typedef struct b200_exchange
+    {
+        void* base[B200_EXCHANGE_MAX_RANKS];
+        uint32_t world;
+        uint32_t rank;
+    } b200_exchange;
+    int b200_dot_allranks_f64(b200_stream_t s, double const* a, double const* b, uint64_t n, double* out_dev, void* scratch, b200_exchange const* ex, uint32_t step);
+    int b200_dot_allranks_f32(b200_stream_t s, float const* a, float const* b, uint64_t n, float* out_dev, void* scratch, b200_exchange const* ex, uint32_t step);
+    int b200_reduce_sum_allranks_u32(b200_stream_t s, uint32_t const* in, uint64_t n, uint32_t* out_dev, void* scratch, b200_exchange const* ex, uint32_t step);
+    int b200_reduce_sum_allranks_f32(b200_stream_t s, float const* in, uint64_t n, float* out_dev, void* scratch, b200_exchange const* ex, uint32_t step);
+    int b200_reduce_sum_allranks_f64(b200_stream_t s, double const* in, uint64_t n, double* out_dev, void* scratch, b200_exchange const* ex, uint32_t step);
+    /* 0, or 1 + rank whose flag never arrived in some call. Synchronous. */
+    int b200_exchange_status(int dev, void const* own_exchange_buffer, uint32_t* status);
+
     /* ---------------------------------------------------------------------------------------------
      * heatEquation2D: one fused FTCS step = StencilKernel (StencilKernel.hpp:31-89) + BoundaryKernel
      * (BoundaryKernel.hpp:24-86) in a single persistent TMA-pipelined kernel.

@@ -64,6 +64,18 @@ def main():
     full = ol.fill("hash_u32", n, seed=9)
     assert int(t.item()) % 2**32 == int(full.astype(np.uint64).sum()) % 2**32, "sharded reduce differs"
 
+    # ---- the same Dot and reduce with the exchange FUSED into the reduction launch (peer stores + flags, no NCCL)
+    ex = multi.ScalarExchange(q, rank, world)
+    multi.connect_exchange_over_process_group(ex, dist)
+    for _ in range(3):  # repeated collective calls (slot double-buffering)
+        d_fused = float(ex.dot(q, da, db))
+        assert d_fused == d_total, f"fused Dot exchange {d_fused} differs from the rank-ordered combination {d_total}"
+        r_fused = int(ex.reduce_sum(q, dx_))
+        assert r_fused == int(t.item()) % 2**32, "fused reduce exchange differs"
+    assert ex.status() == 0
+    dist.barrier()
+    ex.close()
+
     # ---- decomposed heat, IPC peer pointers, fused halo exchange
     py, px = decomp.process_grid(world)
     NY, NX, steps = 192 * py, 640 * px, 25
