@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "build", "conformance")
-EXPECTED = ["integ_axpy", "integ_cudaOnly", "integ_hostOnlyAPI", "integ_mandelbrot", "integ_matMul", "integ_sharedMem", "unit_event", "unit_exec",
+EXPECTED = ["integ_axpy", "integ_cudaOnly", "integ_separableCompilation", "integ_hostOnlyAPI", "integ_mandelbrot", "integ_matMul", "integ_sharedMem", "unit_event", "unit_exec",
             "unit_mem_buf", "unit_mem_copy", "unit_mem_p2p", "unit_mem_view", "unit_queue", "unit_runtime", "unit_traits", "unit_acc", "unit_atomic", "unit_block_shared", "unit_block_sharedSharing",
             "unit_block_sync", "unit_dev", "unit_idx", "unit_intrinsic", "unit_kernel", "unit_mem_fence", "unit_vec",
             "unit_warp", "unit_workDiv"]
