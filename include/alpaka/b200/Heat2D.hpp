@@ -157,6 +157,9 @@ namespace alpaka::b200
     //! (2..4) time levels and exchanges `levels` ghost rows per side straight from the kernel into the neighbour's
     //! array (peer stores + flag words: b200_heat2d_slab_plan_create / b200_heat2d_step2_halo_f64 /
     //! b200_heat2d_stepn_halo_f64). The multi-process form of the same thing is alpaka_b200.multi.HeatSlab.
+    //! Several slabs on ONE device are meant for tests on small fields: the launches of different slabs wait for each
+    //! other's flag words and therefore have to be co-resident, which holds as long as the strip tiles of one launch
+    //! (two tile rows) do not fill the device.
     //! Host fields are (NY+2) x (NX+2) doubles, rows unpadded, as the reference driver's host buffer.
     class Heat2DSlabs
     {
