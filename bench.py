@@ -155,10 +155,25 @@ def time_port_triad(n: int, runs: int):
     return out, host_threads()
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm must use all the host threads it can. Set the
+    environment before the OpenMP runtime of oracle/_ref initialises, and the runtime's ICV in case it already has."""
+    nthreads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(nthreads))
+    except OSError:
+        pass
+    return nthreads
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    use_all_host_threads()
     n_full = 1 << 30
     n = args.n or n_full
     # 3 arrays of n doubles must fit the host comfortably
@@ -470,6 +485,7 @@ def run_ours(args):
     # ---- CPU baseline beside it (rank 0, N=1 only): reference AccCpuOmp2Blocks Triad at C1's 2^25
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        use_all_host_threads()
         n_cpu, runs = 1 << 25, 21
         secs, threads, err = time_reference_triad(n_cpu, runs)
         kind = "reference"
