@@ -47,7 +47,7 @@ def main():
     dx, dy = 1.0 / (nx + 1), 1.0 / (ny + 1)
     dt = 0.2 * min(dx * dx, dy * dy)
     h = ab.heat2d.Heat2D(q, ny, nx, dx, dy, dt)
-    h.upload(np.zeros((ny + 2, nx + 2)))
+    h.upload(ab.heat2d.initial_field(ny, nx, dx, dy))  # real data: power draw depends on the operand bits
     ms1 = timed(q, dev, lambda: h.step(1))
     print(f"one step per launch            {ny}x{nx}: {ms1 * 1e3:8.1f} us/step  {16.0 * ny * nx * 1e-9 / (ms1 * 1e-3):8.1f} GB/s")
     for ty, rpt in ((32, 8), (32, 16), (32, 32), (64, 16), (64, 32)):
@@ -62,6 +62,18 @@ def main():
         msn = timed(q, dev, lambda: h.step(levels, fuse=levels))
         print(f"{levels} steps per launch rpt={rpt:2d} nwy={nwy} {ny}x{nx}: {msn * 1e3 / levels:8.1f} us/step  "
               f"{levels * 16.0 * ny * nx * 1e-9 / (msn * 1e-3):8.1f} GB/s algorithmic  ({msn * 1e3:.1f} us/launch, x{levels * ms1 / msn:.2f})")
+    # sustained: 1000 steps in one go (BASELINE.json's heat configs); the power cap decides here, not the burst figure
+    print("sustained, 1000 steps per measurement (after 1000 warm-up steps):")
+    for levels, rpt, nwy in ((1, 0, 0), (2, 0, 0), (3, 16, 2), (3, 16, 4), (3, 32, 2), (4, 16, 4)):
+        if levels >= 3:
+            ab.runtime.tune_set("heat.stepn_rpt", rpt)
+            ab.runtime.tune_set("heat.stepn_nwy", nwy)
+        if levels == 2:
+            ab.runtime.tune_set("heat.step2_ty", 64)
+            ab.runtime.tune_set("heat.step2_rpt", 16)
+        n = 1000 - 1000 % levels
+        ms = timed(q, dev, lambda: h.step(n, fuse=levels), steps=1, warm=1) / n
+        print(f"  {levels} level(s) per launch rpt={rpt:2d} nwy={nwy}: {ms * 1e3:8.1f} us/step  {16.0 * ny * nx * 1e-9 / (ms * 1e-3):8.1f} GB/s algorithmic")
     h.close()
 
 

@@ -17,3 +17,7 @@ ALPAKA_B200_NATIVE=0 ./babelstream_b200 --array-size=1073741824 --number-runs=10
 ./heat2d_b200 --ny=16384 --nx=16384 --steps=200 --mode=functors
 ./heat2d_b200 --ny=16384 --nx=16384 --steps=200 --mode=fused
 ALPAKA_B200_NATIVE=0 ./heat2d_b200 --ny=16384 --nx=16384 --steps=100 --mode=functors
+./heat2d_b200 --ny=16384 --nx=16384 --steps=300 --mode=fused2
+./heat2d_b200 --ny=16384 --nx=16384 --steps=300 --mode=fused3
+./heat2d_b200 --ny=16384 --nx=16384 --steps=300 --mode=slabs --slabs=1 --levels=3
+for e in heatEquation vectorAdd convolution1D convolution2D parallelLoopPatterns; do ./ref_ex_$e | tail -2; done
