@@ -7,7 +7,7 @@ TAG=${1:-r01}; shift || true
 KERNELS=${@:-triad copy dot heat}
 OUT=gpurun_out/ncu_$TAG
 mkdir -p $OUT
-BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu"
+BENCH="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-sustained"
 for k in $KERNELS; do
   case $k in
     triad)      PAT='regex:TriadOp';      SKIP=3; EXTRA="--quick";;
