@@ -720,10 +720,42 @@ namespace
         int32_t sendRows; // border rows stored into each neighbour = depth of the ghost rows (>= S)
     };
 
+    // One row of one level as a thread holds it: its own pair and the PRODUCTS the stencil needs from it. Every product
+    // v*rX serves two cells (as the right term of the cell on its left and the left term of the cell on its right), every
+    // v*rY two rows (down term of the row above, up term of the row below): computing each once leaves 3 multiplications
+    // per cell instead of 5 -- the same IEEE products, so the sums are bit-identical -- and lanes exchange products, not
+    // values.
     struct RowN
     {
-        double x, y, l, r; // own pair, left neighbour's .y, right neighbour's .x
+        double x, y; // own pair
+        double xh, yh; // x*rX, y*rX
+        double xv, yv; // x*rY, y*rY
+        double lh, rh; // left neighbour's y*rX, right neighbour's x*rX
     };
+
+    __device__ __forceinline__ RowN makeRowN(double x, double y, double rX, double rY)
+    {
+        RowN r;
+        r.x = x;
+        r.y = y;
+        r.xh = __dmul_rn(x, rX);
+        r.yh = __dmul_rn(y, rX);
+        r.xv = __dmul_rn(x, rY);
+        r.yv = __dmul_rn(y, rY);
+        r.lh = r.rh = 0.0;
+        return r;
+    }
+
+    // StencilKernel.hpp:84-86 on precomputed products: ((((c*k + l*rX) + r*rX) + u*rY) + d*rY)
+    __device__ __forceinline__ double ftcsP(double c, double k, double lh, double rh, double uv, double dv)
+    {
+        double t = __dmul_rn(c, k);
+        t = __dadd_rn(t, lh);
+        t = __dadd_rn(t, rh);
+        t = __dadd_rn(t, uv);
+        t = __dadd_rn(t, dv);
+        return t;
+    }
 
     __device__ __forceinline__ double shflUp1(double v)
     {
@@ -760,7 +792,7 @@ namespace
         double const* p = box + size_t(r0) * G::BOXX + (bc - 2);
         bool const storeLane = lane >= G::M / 2 && lane < 32 - G::M / 2;
 
-        double U[S][2]; // level l: the row two above the newest one (own pair)
+        double U[S][2]; // level l: the row two above the newest one -- only its x*rY, y*rY are still needed
         RowN C[S]; //              the row one above the newest one
 #pragma unroll
         for(int i = 0; i < RPT + 2 * S; ++i)
@@ -768,7 +800,9 @@ namespace
             // level 0, tile row r0 - S + i
             double2 const a = lds128(p + size_t(i) * G::BOXX), b = lds128(p + size_t(i) * G::BOXX + 2),
                           c = lds128(p + size_t(i) * G::BOXX + 4);
-            RowN N{b.x, b.y, a.y, c.x};
+            RowN N = makeRowN(b.x, b.y, A.rX, A.rY);
+            N.lh = __dmul_rn(a.y, A.rX);
+            N.rh = __dmul_rn(c.x, A.rX);
 #pragma unroll
             for(int l = 0; l < S; ++l)
             {
@@ -776,15 +810,15 @@ namespace
                 if(i < 2 * (l + 1))
                 {
                     // not enough rows yet: just roll
-                    U[l][0] = C[l].x;
-                    U[l][1] = C[l].y;
+                    U[l][0] = C[l].xv;
+                    U[l][1] = C[l].yv;
                     C[l] = N;
                     break;
                 }
-                double vx = ftcs(C[l].x, C[l].l, C[l].y, U[l][0], N.x, A.k, A.rX, A.rY);
-                double vy = ftcs(C[l].y, C[l].x, C[l].r, U[l][1], N.y, A.k, A.rX, A.rY);
-                U[l][0] = C[l].x;
-                U[l][1] = C[l].y;
+                double vx = ftcsP(C[l].x, A.k, C[l].lh, C[l].yh, U[l][0], N.xv);
+                double vy = ftcsP(C[l].y, A.k, C[l].xh, C[l].rh, U[l][1], N.yv);
+                U[l][0] = C[l].xv;
+                U[l][1] = C[l].yv;
                 C[l] = N;
                 int32_t const gj = y0 + r0 - S + i - (l + 1); // row of the new level-(l+1) values
                 // rows on which level l+1 is defined: the core rows, and on a side with a neighbour the S-(l+1) rows
@@ -800,7 +834,9 @@ namespace
                         if(!(jDefined && gi + 1 >= 1 && gi + 1 <= int32_t(A.nx)))
                             vy = ringOrZeroN(A, gj, gi + 1, jLo, jHi, A.tf[l]);
                     }
-                    N = RowN{vx, vy, shflUp1(vy), shflDown1(vx)};
+                    N = makeRowN(vx, vy, A.rX, A.rY);
+                    N.lh = shflUp1(N.yh);
+                    N.rh = shflDown1(N.xh);
                 }
                 else
                 {

@@ -87,7 +87,8 @@ class Heat2D:
         self.cur = 0
 
     #: time levels per launch that `step(n, fuse=True)` aims for (1..4); tests and tools override it per call
-    DEFAULT_FUSE = 3  # measured best at 16384^2: 1 -> 623, 2 -> 318, 3 -> 212, 4 -> 224 us per step (profiles/r01)
+    DEFAULT_FUSE = 4  # measured at 16384^2, cold burst / the full 1000 steps under the power cap, us per step:
+    #                   1 -> 624 / 672, 2 -> 328 / 372, 3 -> 220 / 241, 4 -> 199 / 221 (profiles/r01/heat_cold_probe.log)
 
     def step(self, n: int = 1, *, fuse=True) -> None:
         """n FTCS steps. `fuse` (stand-alone fields): up to `fuse` steps (True = DEFAULT_FUSE, False = 1) go through ONE

@@ -153,7 +153,7 @@ class HeatSlab(_HaloWiring):
     rows are G..ny+G-1. Same wiring calls as HeatTile (export / open_peer / connect, connect_over_process_group,
     connect_in_process)."""
 
-    DEFAULT_LEVELS = 3
+    DEFAULT_LEVELS = 4
 
     def __init__(self, queue: Queue, rank: int, world: int, NY: int, NX: int, dt: Optional[float] = None,
                  levels: Optional[int] = None):

@@ -10,7 +10,7 @@
 //                     ALPAKA_B200_NATIVE=0)
 //   --mode=fused      per step: one launch of the fused native kernel (alpaka::b200::Heat2DStepper)
 //   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
-//   --mode=fused3     per THREE steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
+//   --mode=fused3 / fused4   per THREE / FOUR steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
 //                     a remainder runs in shallower launches); same bits
 //   --mode=slabs      --slabs=K row slabs of the field in this process, slab k on device k % (number of devices), --levels=G
 //                     (2..4) time levels per launch and per ghost-row exchange (alpaka::b200::Heat2DSlabs); same bits
@@ -143,9 +143,9 @@ auto main(int argc, char** argv) -> int
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);
         }
-        else if(mode == "fused2" || mode == "fused3")
+        else if(mode == "fused2" || mode == "fused3" || mode == "fused4")
         {
-            int const depth = mode == "fused2" ? 2 : 3;
+            int const depth = mode == "fused2" ? 2 : (mode == "fused3" ? 3 : 4);
             alpaka::b200::Heat2DStepper stepper(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
             stepper.steps(computeQueue, numTimeSteps, depth);
             launches = (numTimeSteps + depth - 1) / depth;
@@ -160,7 +160,7 @@ auto main(int argc, char** argv) -> int
             std::vector<alpaka::DevB200> devs;
             for(unsigned k = 0; k < K; ++k)
                 devs.push_back(alpaka::getDevByIdx(alpaka::Platform<Acc>{}, k % nDev));
-            alpaka::b200::Heat2DSlabs slabs(devs, ny, nx, dx, dy, dt, static_cast<int>(args.u64("levels", 3)));
+            alpaka::b200::Heat2DSlabs slabs(devs, ny, nx, dx, dy, dt, static_cast<int>(args.u64("levels", 4)));
             slabs.upload(uBufHost.data());
             auto const ts = std::chrono::high_resolution_clock::now();
             slabs.steps(numTimeSteps);

@@ -113,10 +113,10 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
-        //! `n` steps with up to `depth` (1..4; measured best: 3) time levels per launch; a remainder runs in shallower
+        //! `n` steps with up to `depth` (1..4; measured best: 4) time levels per launch; a remainder runs in shallower
         //! launches (4 = 2 + 2 rather than 3 + 1)
         template<typename TQueue>
-        void steps(TQueue& queue, std::uint32_t n, int depth = 3)
+        void steps(TQueue& queue, std::uint32_t n, int depth = 4)
         {
             if(depth < 1 || depth > 4)
                 throw std::runtime_error("Heat2DStepper::steps: between 1 and 4 time levels per launch");
@@ -169,7 +169,7 @@ namespace alpaka::b200
         using BufFlags = BufB200<std::uint32_t, DimInt<1u>, Idx>;
         using Queue = QueueB200<NonBlocking>;
 
-        Heat2DSlabs(std::vector<DevB200> const& devs, Idx NY, Idx NX, double dx, double dy, double dt, int levels = 3)
+        Heat2DSlabs(std::vector<DevB200> const& devs, Idx NY, Idx NX, double dx, double dy, double dt, int levels = 4)
             : m_NY(NY)
             , m_NX(NX)
             , m_G(static_cast<Idx>(levels))

@@ -189,7 +189,7 @@ def test_reduce_f32_exactly_representable_sums(tmp_path):
 
 
 # ---------------------------------------------------------------------------------- heatEquation2D
-@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("fused2", True, True), ("fused3", True, True), ("functors", True, True),
+@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("fused2", True, True), ("fused3", True, True), ("fused4", True, True), ("functors", True, True),
                                                ("functors", False, False)])
 @pytest.mark.parametrize("shape", [(64, 64), (96, 160)])
 def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
@@ -257,7 +257,7 @@ def test_heat2d_cpp_slabs_on_several_devices(tmp_path):
 
 def test_heat2d_reference_configuration_with_run_time_sizes():
     """The shipped configuration (64x64, 4000 steps, tMax 0.1) through the parameterised driver, both modes."""
-    for mode in ("functors", "fused", "fused2", "fused3"):
+    for mode in ("functors", "fused", "fused2", "fused3", "fused4"):
         r = run("heat2d_b200", "--ny=64", "--nx=64", "--steps=4000", "--dt=2.5e-05", f"--mode={mode}")
         assert "Execution results correct!" in r.stdout
         assert last_json(r.stdout)["max_error"] < 1e-4
