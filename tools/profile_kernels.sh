@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/profile_kernels.sh -- run on the GPU box (under gpurun): one `ncu --set full` capture per hot-path kernel,
 # raw-page CSV extracted next to the report. Usage: tools/profile_kernels.sh <tag> [kernel ...]
-# Kernels: triad copy init nstream dot reduce_u32 heat heat2 heat3 (heat2 / heat3 = two / three time levels per launch)
+# Kernels: triad copy init nstream dot reduce_u32 heat heat2 heat3 heat4 (heatN = N time levels per launch)
 set -u
 TAG=${1:-r01}; shift || true
 KERNELS=${@:-triad copy dot heat}
@@ -18,7 +18,8 @@ for k in $KERNELS; do
     reduce_u32) PAT='regex:reduceKernel<unsigned'; SKIP=3; EXTRA="";;
     heat)       PAT='regex:heatStepKernel'; SKIP=5; EXTRA="";;
     heat2)      PAT='regex:heatStep2Kernel'; SKIP=5; EXTRA="";;
-    heat3)      PAT='regex:heatStepNKernel'; SKIP=5; EXTRA="";;
+    heat3)      PAT='regex:heatStepNKernel<.int.3'; SKIP=5; EXTRA="";;
+    heat4)      PAT='regex:heatStepNKernel<.int.4'; SKIP=5; EXTRA="";;
     *) echo "unknown kernel $k"; continue;;
   esac
   timeout 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "$PAT" -s $SKIP -c 1 -f -o $OUT/$k $BENCH $EXTRA > $OUT/$k.log 2>&1
