@@ -668,20 +668,23 @@ namespace
 
 
     // ------------------------------------------------------------------------------------------------------------
-    // S time levels per launch, S >= 3 (deeper temporal blocking). Recomputing the neighbours' columns as the two-level
-    // kernel does costs (S+1) S stencils per pair-row and would make three levels FP64-bound, so here every thread
-    // computes ONLY its own column pair at every level and takes the two horizontal neighbours' values from the adjacent
-    // lanes by warp shuffle. A warp owns a window of 64 columns; what the edge lanes cannot obtain becomes invalid one
-    // column per level, so after S levels the warp stores the inner 64 - 2M columns (M = 2 (S/2): pairs stay aligned)
-    // and neighbouring warps' windows overlap by 2M columns -- 6.7 % redundant work at S = 3.
+    // S time levels per launch, S = 3 or 4 (deeper temporal blocking; 4 is the default depth). Recomputing the neighbours'
+    // columns as the two-level kernel does costs (S+1) S stencils per pair-row and would make three levels FP64-bound, so
+    // here every thread computes ONLY its own column pair at every level and takes what it needs from the adjacent lanes
+    // by warp shuffle. A warp owns a window of 64 columns; what the edge lanes cannot obtain becomes invalid one column per
+    // level, so after S levels the warp stores the inner 64 - 2M columns (M = 2 (S/2): pairs stay aligned) and neighbouring
+    // warps' windows overlap by 2M columns -- 6.7 % redundant work at S = 3, 14 % at S = 4.
     //   * tile = NWY x RPT rows by NWX x (64 - 2M) columns; its (rows + 2S) x (columns + 2M + 4) input box arrives by ONE
     //     TMA copy (S = 3: 128 columns = 1 KB per row), zero-filled outside the field;
     //   * a thread walks down its rows once: per input row 3 LDS.128 (own pair + the pairs left and right of it), then one
     //     pair of stencils per level as soon as three rows of the level below exist; rows roll through registers;
-    //     per level and row two 64-bit shuffles. FP64 work per pair-row at S = 3, RPT 16: 2 x (20 + 18 + 16) / 16 x 64/60 =
-    //     7.2 stencils for THREE steps (the one-step kernel needs 2 per step).
+    //   * every product v*rX / v*rY is computed ONCE per value and shared by the two cells / two rows whose stencils use it
+    //     (RowN): 3 multiplications + 4 additions per cell and level instead of 5 + 4, the same IEEE products and the same
+    //     order of additions, hence the same bits. Lanes exchange the products (two 64-bit shuffles per level and row).
+    //     FP64 instructions per output pair-row at S = 4, RPT 16: about 62 for FOUR steps (the one-step kernel issues 18 per
+    //     step); that is what made four levels per launch faster than three.
     //   * ring cells of intermediate level k take tf[k] * (sx + sy); only tiles touching the field edge test per cell.
-    // Stand-alone fields only.
+    // Stand-alone fields (padY = 1) and row slabs whose ghost rows are at least S deep (padY >= S, fused halo exchange).
     constexpr int kMaxLevels = 4;
 
     template<int S>
