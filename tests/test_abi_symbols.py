@@ -64,3 +64,34 @@ def test_package_never_imports_the_oracle():
         for f in files:
             text = open(os.path.join(dirpath, f), errors="ignore").read()
             assert "hotpath_oracle" not in text and "liboracle" not in text, f
+
+
+def test_argument_validation_of_the_fused_entries_needs_no_device():
+    """Bad arguments are refused (B200_EINVAL = -1) before any CUDA call: null plans, missing exchange descriptors, slab
+    plans that are not slabs, too many ranks. Also true on a box without a GPU."""
+    import numpy as np
+
+    lib = _lib.load()
+    EINVAL = -1
+    tf = (ctypes.c_double * 4)(1.0, 1.0, 1.0, 1.0)
+    assert lib.b200_heat2d_step2_f64(None, None, 0, 0.1, 0.1, 1.0, 1.0) == EINVAL
+    assert lib.b200_heat2d_stepn_f64(None, None, 0, 0.1, 0.1, 3, tf) == EINVAL
+    assert lib.b200_heat2d_step2_halo_f64(None, None, 0, 0.1, 0.1, 1.0, 1.0, 1) == EINVAL
+    assert lib.b200_heat2d_stepn_halo_f64(None, None, 0, 0.1, 0.1, 4, tf, 1) == EINVAL
+    # a slab keeps the full width (LEFT | RIGHT physical), at least 2 * ghost rows, ghost depth 2..4
+    sx, sy = np.zeros(66), np.zeros(72)
+    plan = ctypes.c_void_p()
+    fake = ctypes.c_void_p(256)  # never dereferenced: the checks below fail first
+    for edges, ny, ghost in ((1 | 2, 64, 2), (4 | 8, 3, 2), (4 | 8, 64, 1), (4 | 8, 64, 5)):
+        rc = lib.b200_heat2d_slab_plan_create(0, fake, fake, 66 * 8 + 16, ny, 64, sx.ctypes.data, sy.ctypes.data, edges, ghost,
+                                              ctypes.byref(plan))
+        assert rc == EINVAL, (edges, ny, ghost, rc)
+    out = ctypes.c_void_p(256)
+    assert lib.b200_dot_allranks_f64(None, fake, fake, 16, out, fake, None, 1) == EINVAL  # no exchange descriptor
+    ex = _lib.Exchange()
+    ex.world, ex.rank = 17, 0  # more ranks than B200_EXCHANGE_MAX_RANKS
+    assert lib.b200_reduce_sum_allranks_u32(None, fake, 16, out, fake, ctypes.byref(ex), 1) == EINVAL
+    ex.world, ex.rank = 2, 0  # step 0 is not a call number; base[1] missing
+    assert lib.b200_reduce_sum_allranks_u32(None, fake, 16, out, fake, ctypes.byref(ex), 0) == EINVAL
+    ex.base[0] = 256
+    assert lib.b200_reduce_sum_allranks_u32(None, fake, 16, out, fake, ctypes.byref(ex), 1) == EINVAL
