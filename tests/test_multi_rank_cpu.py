@@ -335,3 +335,47 @@ def test_slab_decomposed_heat_over_gloo(tmp_path, world, ghost, steps):
     for r in range(world):
         decomp.slab_for(r, world, NY, NX, ghost).stitch(out, np.load(tmp_path / f"slab{r}.npy"))
     assert out.tobytes() == want.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------ property tests
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+
+@settings(max_examples=300, deadline=None)
+@given(n=st.integers(0, 5000), depth=st.integers(1, 4), min_depth=st.integers(1, 2))
+def test_launch_schedule_properties(n, depth, min_depth):
+    if depth < min_depth:
+        depth = min_depth
+    impossible = min_depth == 2 and (n == 1 or (depth == 2 and n % 2 == 1))
+    if impossible:
+        with pytest.raises(ValueError):
+            decomp.launch_schedule(n, depth, min_depth)
+        return
+    sched = decomp.launch_schedule(n, depth, min_depth)
+    assert sum(sched) == n and all(min_depth <= k <= depth for k in sched)
+    assert len(sched) <= -(-n // depth) + 1
+    assert sched == sorted(sched, reverse=True)  # deep launches first, the shallow tail last
+
+
+@settings(max_examples=200, deadline=None)
+@given(world=st.integers(1, 8), ghost=st.integers(1, 4), rows_per_ghost=st.integers(2, 6), NX=st.integers(1, 50), data=st.data())
+def test_slab_geometry_properties(world, ghost, rows_per_ghost, NX, data):
+    ny = ghost * rows_per_ghost
+    NY = ny * world
+    rank = data.draw(st.integers(0, world - 1))
+    s = decomp.slab_for(rank, world, NY, NX, ghost)
+    assert s.shape == (ny + 2 * ghost, NX + 2) and s.g0 == rank * ny - (ghost - 1)
+    j0, j1 = s.owned_rows()
+    # owned rows in global padded coordinates: the core rows, plus ring row 0 on the first / NY+1 on the last slab
+    lo, hi = s.g0 + j0, s.g0 + j1
+    assert lo == (0 if rank == 0 else rank * ny + 1) and hi == (NY + 2 if rank == world - 1 else (rank + 1) * ny + 1)
+    # ghost rows of neighbouring slabs are exactly the other's border rows
+    if rank + 1 < world:
+        t = decomp.slab_for(rank + 1, world, NY, NX, ghost)
+        mine = range(s.g0 + s.send_rows("bottom").start, s.g0 + s.send_rows("bottom").stop)
+        theirs = range(t.g0 + t.recv_rows("top").start, t.g0 + t.recv_rows("top").stop)
+        assert list(mine) == list(theirs)
+        back = range(t.g0 + t.send_rows("top").start, t.g0 + t.send_rows("top").stop)
+        here = range(s.g0 + s.recv_rows("bottom").start, s.g0 + s.recv_rows("bottom").stop)
+        assert list(back) == list(here)
