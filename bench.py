@@ -398,7 +398,11 @@ def run_ours(args):
             # step of ALGORITHMIC bytes, a half / a third / a quarter of them actually moved, so the fraction of the HBM peak exceeds 1
             for G in (4, 3, 2):  # the default depth first, on a board that is still cool
                 record(f"heat2d_f64_{G}_steps_per_launch", timed(lambda: h.step(G, fuse=G), max(20, K), 5), G * 16.0 * NY * NX)
-                kernels[f"heat2d_f64_{G}_steps_per_launch"]["ms_per_step"] = round(kernels[f"heat2d_f64_{G}_steps_per_launch"]["ms"] / G, 4)
+                kG = kernels[f"heat2d_f64_{G}_steps_per_launch"]
+                kG["ms_per_step"] = round(kG["ms"] / G, 4)
+                # what one launch actually moves: one read + one write of the field (ncu: 4.25 GB at 16384^2), whatever G
+                kG["hbm_pass_gbs"] = round(16.0 * NY * NX * 1e-9 / (kG["ms"] * 1e-3), 1)
+                kG["hbm_pass_frac_of_peak"] = round(kG["hbm_pass_gbs"] / peak, 4)
             # BASELINE.json configs[3] as specified: 1000 FTCS steps in one go (sustained clocks, not a short burst)
             for G in (() if args.no_sustained else (1, 4)):
                 ms_step, clk = timed_run(lambda: h.step(1000, fuse=G), 1000)
