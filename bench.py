@@ -315,7 +315,8 @@ def run_ours(args):
         kernels[name] = {"gbs": round(gbs, 1), "ms": round(ms, 4), "frac_of_hbm_peak": round(gbs / world / peak, 4)}
 
     record("triad_f64", ms_triad, triad_bytes)
-    if not args.quick:
+    exch = None
+    if not args.quick and not args.only_heat:
         Ks = max(5, K // 2)
         record("init_f64", timed(lambda: bs.init(q, a, b, c), Ks, 3), 24.0 * n)
         bs.copy(q, a, b)
@@ -349,38 +350,39 @@ def run_ours(args):
     q.wait()
 
     if not args.quick:
-        # ---- example/reduce: 2^32 uint32 (17.2 GB) and 2^30 float (BASELINE.json configs[2])
-        nr = (1 << 32) if not args.n else 4 * n
-        src = ab.alloc_buf(dev, np.uint32, nr, q)
-        res = ab.alloc_buf(dev, np.uint32, 1, q)
-        # fill with ones via the f32 init kernel's bit pattern is not exact for u32; memset 0x01010101 instead
-        ab.memset(q, src, 1)
-        Ks = max(5, K // 2)
-        if exch is None:
-            record("reduce_u32", timed(lambda: ab.reduce.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
-        else:
-            record("reduce_u32", timed(lambda: exch.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
-            kernels["reduce_u32"]["exchange"] = kernels["dot_f64"]["exchange"]
-        got = np.empty(1, dtype=np.uint32)
-        ab.memcpy(q, got, res)
-        q.wait()
-        assert int(got[0]) == (0x01010101 * nr * world) % 2**32, "reduce u32 check failed"
-        src.free()
-        res.free()
-        nf = (1 << 30) if not args.n else n
-        srcf = ab.alloc_buf(dev, np.float32, nf, q)
-        resf = ab.alloc_buf(dev, np.float32, 1, q)
-        ab.memset(q, srcf, 0)
-        if exch is None:
-            record("reduce_f32", timed(lambda: ab.reduce.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
-        else:
-            record("reduce_f32", timed(lambda: exch.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
-            kernels["reduce_f32"]["exchange"] = kernels["dot_f64"]["exchange"]
-            assert exch.status() == 0, "a rank's flag never arrived in the fused Dot/reduce exchange"
-            barrier()
-            exch.close()
-        for bf in (srcf, resf):
-            bf.free()
+        if not args.only_heat:
+            # ---- example/reduce: 2^32 uint32 (17.2 GB) and 2^30 float (BASELINE.json configs[2])
+            nr = (1 << 32) if not args.n else 4 * n
+            src = ab.alloc_buf(dev, np.uint32, nr, q)
+            res = ab.alloc_buf(dev, np.uint32, 1, q)
+            # fill with ones via the f32 init kernel's bit pattern is not exact for u32; memset 0x01010101 instead
+            ab.memset(q, src, 1)
+            Ks = max(5, K // 2)
+            if exch is None:
+                record("reduce_u32", timed(lambda: ab.reduce.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+            else:
+                record("reduce_u32", timed(lambda: exch.reduce_sum_async(q, src, res), Ks, 3), 4.0 * nr)
+                kernels["reduce_u32"]["exchange"] = kernels["dot_f64"]["exchange"]
+            got = np.empty(1, dtype=np.uint32)
+            ab.memcpy(q, got, res)
+            q.wait()
+            assert int(got[0]) == (0x01010101 * nr * world) % 2**32, "reduce u32 check failed"
+            src.free()
+            res.free()
+            nf = (1 << 30) if not args.n else n
+            srcf = ab.alloc_buf(dev, np.float32, nf, q)
+            resf = ab.alloc_buf(dev, np.float32, 1, q)
+            ab.memset(q, srcf, 0)
+            if exch is None:
+                record("reduce_f32", timed(lambda: ab.reduce.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+            else:
+                record("reduce_f32", timed(lambda: exch.reduce_sum_async(q, srcf, resf), Ks, 3), 4.0 * nf)
+                kernels["reduce_f32"]["exchange"] = kernels["dot_f64"]["exchange"]
+                assert exch.status() == 0, "a rank's flag never arrived in the fused Dot/reduce exchange"
+                barrier()
+                exch.close()
+            for bf in (srcf, resf):
+                bf.free()
 
         # ---- heatEquation2D 16384^2 double (BASELINE.json configs[3]); 16 B per core cell per step.
         # N = 1: the plain fused step. N > 1: STRONG scaling of the same 16384^2 field, Py x Px decomposition, halo
@@ -569,6 +571,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="Triad only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--only-heat", action="store_true", help="Triad headline + the heatEquation2D lines only")
     ap.add_argument("--no-sustained", action="store_true", help="skip the 1000-step heat runs (profiling under ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
