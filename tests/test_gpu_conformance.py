@@ -9,7 +9,8 @@ WorkDivMembers), atomic (all ops x types x hierarchies), kernel (lambdas, templa
 intrinsic (popcount, ffs), mem/fence, acc (names, device properties, traits), dev, integ/axpy, integ/sharedMem;
 mem/buf, mem/copy (3-D slicing), mem/view (sub-views, ViewConst, plain pointers, device globals), mem/p2p, queue, event,
 traits, runtime; exec (uniformElements / uniformGroups / independentGroups / uniformElementsND / oncePerGrid ...:
-SURVEY.md section 8f row 3); integ/matMul, integ/mandelbrot, integ/hostOnlyAPI, integ/cudaOnly (CUDA-only mode).
+SURVEY.md section 8f row 3); integ/matMul, integ/mandelbrot, integ/hostOnlyAPI, integ/cudaOnly (CUDA-only mode),
+integ/separableCompilation (relocatable device code); the host-only groups unit/meta and unit/core.
 The binaries are built where the reference tree exists and travel with the snapshot; a missing binary FAILS."""
 import os
 import subprocess
@@ -20,7 +21,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "build", "conformance")
-EXPECTED = ["integ_axpy", "integ_cudaOnly", "integ_separableCompilation", "integ_hostOnlyAPI", "integ_mandelbrot", "integ_matMul", "integ_sharedMem", "unit_event", "unit_exec",
+EXPECTED = ["unit_meta", "unit_core", "integ_axpy", "integ_cudaOnly", "integ_separableCompilation", "integ_hostOnlyAPI", "integ_mandelbrot", "integ_matMul", "integ_sharedMem", "unit_event", "unit_exec",
             "unit_mem_buf", "unit_mem_copy", "unit_mem_p2p", "unit_mem_view", "unit_queue", "unit_runtime", "unit_traits", "unit_acc", "unit_atomic", "unit_block_shared", "unit_block_sharedSharing",
             "unit_block_sync", "unit_dev", "unit_idx", "unit_intrinsic", "unit_kernel", "unit_mem_fence", "unit_vec",
             "unit_warp", "unit_workDiv"]
