@@ -1,0 +1,74 @@
+"""Properties of the COMPILED kernels that the design relies on, checked on the CPU box from the objects and ptxas logs that
+__graft_entry__.build() leaves under build/csrc (nvcc cross-compiles for sm_100a without a GPU):
+
+  * no fused multiply-add anywhere in the stream, reduction and stencil kernels -- FMA contraction is pinned OFF on both
+    sides of every parity comparison, so a DFMA / FFMA in the SASS would be a parity bug;
+  * the stencil tiles really arrive by TMA (UTMALDG) and the N-level kernel exchanges by warp shuffle;
+  * the stream kernels move 32-byte vectors (the .256 forms new with sm_100);
+  * the default instantiations of the hot kernels do not spill."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "build", "csrc")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+
+def sass(name):
+    path = os.path.join(OBJ, name + ".o")
+    if not os.path.exists(path) or not os.path.exists(CUOBJDUMP):
+        pytest.skip(f"{path} or cuobjdump missing (the GPU box only carries the linked library)")
+    return subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True, check=True).stdout
+
+
+@pytest.mark.parametrize("obj", ["b200_stream", "b200_reduce", "b200_heat2d"])
+def test_no_fused_multiply_add_in_the_hot_path_objects(obj):
+    text = sass(obj)
+    assert "DMUL" in text or "FMUL" in text or "DADD" in text  # the object does hold arithmetic
+    assert not re.search(r"\b[DFH]FMA\b", text), "contraction must stay off: found an FMA in " + obj
+
+
+def test_stencil_tiles_arrive_by_tma_and_levels_exchange_by_shuffle():
+    text = sass("b200_heat2d")
+    assert text.count("UTMALDG") >= 3  # one-level, two-level and N-level kernels
+    assert "SHFL.UP" in text and "SHFL.DOWN" in text
+    assert "SYNCS" in text or "MBARRIER" in text.upper()  # mbarrier-signalled copies
+
+
+def test_streams_use_32_byte_vector_accesses():
+    text = sass("b200_stream")
+    assert re.search(r"LDG\.E[.\w]*\.256", text) and re.search(r"STG\.E[.\w]*\.256", text)
+
+
+def ptxas_entries(name):
+    path = os.path.join(OBJ, name + ".ptxas.log")
+    if not os.path.exists(path):
+        pytest.skip(f"{path} missing")
+    out, cur = {}, None
+    for line in open(path):
+        m = re.search(r"Compiling entry function '([^']+)'", line)
+        if m:
+            cur = m.group(1)
+        m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if m and cur:
+            out[cur] = tuple(int(g) for g in m.groups())
+    return out
+
+
+@pytest.mark.parametrize("obj,needles", [
+    ("b200_stream", ["TriadOpIdEEdLi32ELi1ELi1E", "CopyOpIdEEdLi32ELi1ELi1E", "NstreamOpIdEEdLi32ELi1ELi1E"]),
+    ("b200_reduce", ["reduceKernelIdLb1ELi2E", "reduceKernelIjLb0ELi4E", "reduceKernelIfLb0ELi4E"]),
+    ("b200_heat2d", ["heatStepKernelILi1ELi8E", "heatStep2KernelILi1ELi64ELi16E", "heatStepNKernelILi4ELi16ELi2E",
+                     "heatStepNKernelILi3ELi16ELi2E"]),
+])
+def test_default_instantiations_do_not_spill(obj, needles):
+    entries = ptxas_entries(obj)
+    for needle in needles:
+        hits = {k: v for k, v in entries.items() if needle in k}
+        assert hits, f"no entry function matching {needle} in {obj}"
+        for k, (stack, st, ld) in hits.items():
+            assert (stack, st, ld) == (0, 0, 0), f"{k}: {stack} bytes stack, {st}/{ld} bytes spilled"
