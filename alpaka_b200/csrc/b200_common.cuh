@@ -55,6 +55,41 @@ namespace b200
 #ifdef __CUDACC__
 namespace b200
 {
+    // ---- bounded flag waits of the fused exchanges (Dot / reduce scalar exchange, heat halo exchange).
+    // A peer that died must not hang this GPU for ever, but a peer that is merely late (first-launch module load, a
+    // paused rank) must not produce a wrong result either: the bound is generous (tunable `exchange.timeout_ms`,
+    // default 60 s), a timeout raises the status word the host checks AND poisons the result (NaN for floating point).
+    inline uint64_t waitLimitNs()
+    {
+        return uint64_t(tune("exchange.timeout_ms", 60000)) * 1000000ull;
+    }
+
+    __device__ __forceinline__ uint64_t globalTimerNs()
+    {
+        uint64_t t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+    }
+
+    //! spins until *flag (acquire, system scope) satisfies `flag + slack >= want`; false on timeout
+    __device__ __forceinline__ bool waitFlagAtLeast(uint32_t const* flag, uint32_t want, uint32_t slack, uint64_t limitNs)
+    {
+        uint64_t t0 = 0;
+        for(uint32_t spins = 0;; ++spins)
+        {
+            uint32_t seen;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+            if(seen + slack >= want)
+                return true;
+            if(spins == 64u)
+                t0 = globalTimerNs();
+            else if(spins > 64u && (spins & 63u) == 0u && globalTimerNs() - t0 > limitNs)
+                return false;
+            if(spins > 16u)
+                __nanosleep(spins > 1024u ? 1000 : 100);
+        }
+    }
+
     // ---- 128-bit and 256-bit global accesses with streaming cache policy.
     // HINT: 0 = default, 1 = ld.nc / L1::no_allocate + st .cs (evict-first streaming)
     template<int HINT>

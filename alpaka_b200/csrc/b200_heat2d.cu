@@ -79,6 +79,7 @@ namespace
         uint32_t* myFlags; // [4] slots set by the neighbours: "my step-s border cells are in your ghosts"
         uint32_t* stripCounter; // strip tiles finished in this launch (reset by the last one)
         uint32_t* status; // != 0: a flag wait timed out
+        uint64_t waitNs; // bound of a flag wait (b200::waitLimitNs)
         uint32_t stripTiles;
         uint32_t step; // 1-based time level this launch produces
     };
@@ -178,29 +179,18 @@ namespace
     // ---- the flag protocol of the fused halo exchange, shared by the three kernel families ---------------------------
     // waitForNeighbours: called by ONE thread of a CTA that is about to read ghost cells. The ghosts hold the neighbours'
     // border cells of the previous launch once their flag words say so (which also means the neighbours are done READING
-    // the ghost cells this launch overwrites in their other buffer). Bounded spin (about 2 s): a peer that died must not
-    // hang this GPU. Ends with the proxy fence TMA needs: ghosts are written through the generic proxy (peer stores),
+    // the ghost cells this launch overwrites in their other buffer). Bounded wait (b200::waitLimitNs, 60 s by default): a peer
+    // that died must not hang this GPU; a timeout raises the status word, which the host layers turn into an error. Ends with the proxy fence TMA needs: ghosts are written through the generic proxy (peer stores),
     // the TMA unit reads them through the async proxy.
     template<int SIDES>
-    __device__ __forceinline__ void waitForNeighbours(double* const (&peerDst)[SIDES], uint32_t const* myFlags, uint32_t step, uint32_t* status)
+    __device__ __forceinline__ void waitForNeighbours(double* const (&peerDst)[SIDES], uint32_t const* myFlags, uint32_t step, uint32_t* status, uint64_t waitNs)
     {
         for(int side = 0; side < SIDES; ++side)
         {
             if(peerDst[side] == nullptr)
                 continue;
-            uint32_t seen = 0, spins = 0;
-            for(;;)
-            {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(myFlags + side) : "memory");
-                if(seen + 1u >= step) // seen >= step - 1 without underflow
-                    break;
-                if(++spins > 2000000u)
-                {
-                    atomicExch(status, 1u + uint32_t(side));
-                    break;
-                }
-                __nanosleep(1000);
-            }
+            if(!b200::waitFlagAtLeast(myFlags + side, step, 1u, waitNs)) // seen >= step - 1 without underflow
+                atomicExch(status, 1u + uint32_t(side));
         }
         asm volatile("fence.proxy.async;" ::: "memory");
     }
@@ -260,7 +250,7 @@ namespace
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // Only strip tiles read ghost cells, and they come first in the tile order: CTAs without a strip tile skip the wait
             if(A.myFlags != nullptr && blockIdx.x < A.stripTiles)
-                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
         }
         __syncthreads();
 
@@ -466,6 +456,7 @@ namespace
         uint32_t* myFlags; // slots [0] top, [1] bottom, set by the neighbours
         uint32_t* stripCounter;
         uint32_t* status;
+        uint64_t waitNs;
         uint32_t stripTiles;
         uint32_t step; // 1-based index of this launch
         uint32_t sendRows; // border rows stored into each neighbour = depth of the ghost rows (>= 2)
@@ -638,7 +629,7 @@ namespace
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // strip tiles read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
             if(strip && A.myFlags != nullptr)
-                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
             mbarExpectTx(&full, Step2Geom<TYT>::kBoxBytes);
             tmaLoad2d(smem, &mapSrc, int32_t(x0) - 2, int32_t(y0) - 2, &full);
         }
@@ -718,6 +709,7 @@ namespace
         uint32_t* myFlags;
         uint32_t* stripCounter;
         uint32_t* status;
+        uint64_t waitNs;
         uint32_t stripTiles;
         uint32_t step; // 1-based index of this launch
         int32_t sendRows; // border rows stored into each neighbour = depth of the ghost rows (>= S)
@@ -921,7 +913,7 @@ namespace
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             // strip tiles read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
             if(strip && A.myFlags != nullptr)
-                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status);
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
             mbarExpectTx(&full, kBoxBytes);
             tmaLoad2d(smem, &mapSrc, x0 - G::M - 2, y0 - S, &full);
         }
@@ -1395,6 +1387,7 @@ extern "C"
                 A.myFlags = plan->halo.my_flags;
                 A.stripCounter = plan->haloScratch;
                 A.status = plan->haloScratch + 1;
+        A.waitNs = b200::waitLimitNs();
                 A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
                 A.step = haloStep;
                 // heat.halo_debug (measurement only, results become wrong): 1 = no peer stores, 2 = no flag wait
@@ -1508,6 +1501,7 @@ extern "C"
                 A.myFlags = plan->halo.my_flags;
                 A.stripCounter = plan->haloScratch;
                 A.status = plan->haloScratch + 1;
+        A.waitNs = b200::waitLimitNs();
                 A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
                 A.step = haloStep;
                 int64_t const dbg = b200::tune("heat.halo_debug", 0);
@@ -1656,6 +1650,7 @@ extern "C"
             A.myFlags = nullptr;
         A.stripCounter = plan->haloScratch;
         A.status = plan->haloScratch + 1;
+        A.waitNs = b200::waitLimitNs();
         A.step = step;
         return launchHeat(plan, stream, src_index, A);
     }

@@ -20,6 +20,9 @@
 // oracle's pinned contraction; integer sums wrap (order-free, bit-exact vs the reference).
 #include "b200_common.cuh"
 
+#include <cmath>
+#include <type_traits>
+
 namespace
 {
     using b200::ldg256;
@@ -131,6 +134,7 @@ namespace
     {
         char* base[kMaxRanks]; // base[r]: rank r's exchange buffer as seen from this device; base[rank] is the own one
         uint32_t world, rank, step; // world <= 1: no exchange
+        uint64_t waitNs; // bound of the flag wait (b200::waitLimitNs)
     };
 
     // Called by the threads of the last block after thread 0 produced this device's scalar `mine`. Returns (in thread 0)
@@ -139,8 +143,10 @@ namespace
     __device__ __forceinline__ T exchangeAllRanks(Exchange const& X, T mine, uint64_t* smemSlots)
     {
         __shared__ uint64_t mineBits;
+        __shared__ int timedOut;
         if(threadIdx.x == 0)
         {
+            timedOut = 0;
             uint64_t u = 0;
             memcpy(&u, &mine, sizeof(T));
             mineBits = u;
@@ -155,21 +161,13 @@ namespace
             auto* flag = reinterpret_cast<uint32_t*>(X.base[p] + kFlagsOffset) + X.rank;
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(mineBits) : "memory");
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(X.step) : "memory");
-            // ... and rank p's scalar out of MY buffer once its flag says it has arrived (bounded spin, about 2 s)
+            // ... and rank p's scalar out of MY buffer once its flag says it has arrived (bounded wait, b200::waitLimitNs)
             char* const my = X.base[X.rank];
             auto const* myFlag = reinterpret_cast<uint32_t const*>(my + kFlagsOffset) + p;
-            uint32_t seen = 0, spins = 0;
-            for(;;)
+            if(!b200::waitFlagAtLeast(myFlag, X.step, 0u, X.waitNs))
             {
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(myFlag) : "memory");
-                if(seen >= X.step)
-                    break;
-                if(++spins > 2000000u)
-                {
-                    atomicExch(reinterpret_cast<uint32_t*>(my + kStatusOffset), 1u + p);
-                    break;
-                }
-                __nanosleep(1000);
+                atomicExch(reinterpret_cast<uint32_t*>(my + kStatusOffset), 1u + p);
+                timedOut = 1;
             }
             uint64_t v;
             asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(reinterpret_cast<uint64_t const*>(my) + parity * kMaxRanks + p) : "memory");
@@ -186,6 +184,10 @@ namespace
                 memcpy(&v, &smemSlots[r], sizeof(T));
                 total = addv(total, v);
             }
+            // a peer never arrived: the status word is set; floating-point results are poisoned as well
+            if constexpr(std::is_floating_point_v<T>)
+                if(timedOut)
+                    total = T(NAN);
         }
         return total;
     }
@@ -312,6 +314,7 @@ namespace
             X.world = ex->world;
             X.rank = ex->rank;
             X.step = step;
+            X.waitNs = b200::waitLimitNs();
         }
         B200_REQUIRE(n == 0 || (a && (!DOT || b)), B200_EINVAL);
         B200_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, B200_EALIGN);

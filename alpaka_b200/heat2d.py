@@ -78,11 +78,15 @@ class Heat2D:
 
     def upload(self, field: np.ndarray) -> None:
         """Both buffers start as copies of the field (see oracle/ref_heat2d.cpp on corners)."""
-        field = np.ascontiguousarray(field, dtype=np.float64)
-        if field.shape != (self.ny + 2, self.nx + 2):
+        from .runtime import HostBuf
+
+        if not isinstance(field, HostBuf):  # a pinned HostBuf goes to the device as it is (asynchronous copy)
+            field = np.ascontiguousarray(field, dtype=np.float64)
+        shape = tuple(field.extent) if isinstance(field, HostBuf) else field.shape
+        if shape != (self.ny + 2, self.nx + 2):
             raise B200Error(-1, "heat2d: field must be (ny+2) x (nx+2)")
-        memcpy(self.queue, self.bufs[0], field)
-        memcpy(self.queue, self.bufs[1], field)
+        memcpy(self.queue, self.bufs[0], field)  # one trip over PCIe ...
+        memcpy(self.queue, self.bufs[1], self.bufs[0])  # ... the second copy is device to device
         self.queue.wait()
         self.cur = 0
 
@@ -128,12 +132,16 @@ class Heat2D:
     def current(self) -> Buf:
         return self.bufs[self.cur]
 
-    def download(self) -> np.ndarray:
-        out = np.empty((self.ny + 2, self.nx + 2), dtype=np.float64)
+    def download(self, out=None):
+        """The current field on the host; `out` may be a pinned HostBuf of the field's shape (returned as numpy)."""
+        from .runtime import HostBuf
+
+        if out is None:
+            out = np.empty((self.ny + 2, self.nx + 2), dtype=np.float64)
         self.queue.wait()
         memcpy(self.queue, out, self.current())
         self.queue.wait()
-        return out
+        return out.array if isinstance(out, HostBuf) else out
 
     def close(self) -> None:
         if getattr(self, "plan", None):

@@ -81,6 +81,13 @@ class _HaloWiring:
         check(_lib.load().b200_heat2d_halo_status(self._plan_handle(), C.byref(s)))
         return int(s.value)
 
+    def raise_on_timeout(self) -> None:
+        """A neighbour's flag did not arrive within `exchange.timeout_ms`: ghost cells were read stale, the field is invalid."""
+        s = self.status()
+        if s != 0:
+            raise B200Error(-1, f"heat halo exchange on rank {self.tile.rank}: the neighbour on side '{SIDES[s - 1]}' never "
+                                f"published its time level (flag wait timed out); the field is invalid")
+
     def _close_peers(self) -> None:
         lib = _lib.load()
         for p in self._opened:
@@ -137,7 +144,9 @@ class HeatTile(_HaloWiring):
         self.queue._after_enqueue()
 
     def download(self) -> np.ndarray:
-        return self.h.download()
+        out = self.h.download()
+        self.raise_on_timeout()
+        return out
 
     def close(self) -> None:
         self._close_peers()
@@ -249,6 +258,7 @@ class HeatSlab(_HaloWiring):
         self.queue.wait()
         memcpy(self.queue, out, self.bufs[self.cur])
         self.queue.wait()
+        self.raise_on_timeout()
         return out
 
     def owned_rows(self) -> tuple[int, int]:
@@ -361,7 +371,15 @@ class ScalarExchange:
         memcpy(queue, host, out)
         queue.wait()
         out.free()
+        self.raise_on_timeout()
         return host[0]
+
+    def raise_on_timeout(self) -> None:
+        """A peer's flag did not arrive within `exchange.timeout_ms`: the value on this rank is not the all-ranks sum."""
+        s = self.status()
+        if s != 0:
+            raise B200Error(-1, f"fused Dot/reduce exchange: rank {s - 1}'s scalar never arrived on rank {self.rank} "
+                                f"(flag wait timed out); the result is invalid")
 
     def dot(self, queue: Queue, a: Buf, b: Buf, n: Optional[int] = None):
         from .runtime import alloc_buf

@@ -269,8 +269,14 @@ class Buf:
             lib = _lib.load()
             if self._ipc:
                 lib.b200_free_device(self.dev.idx, self.ptr)
+            elif self._queue is not None:
+                lib.b200_free_async(self.dev.idx, self._queue.handle, self.ptr)
             else:
-                lib.b200_free_async(self.dev.idx, self._queue.handle if self._queue else None, self.ptr)
+                # allocated without a queue: the pool free would be ordered on the legacy NULL stream, which the
+                # (non-blocking) queue streams do not synchronise with. cudaFree semantics instead: wait for the device
+                # first, as the C++ allocBuf deleter does (include/alpaka/b200/Mem.hpp), then release.
+                lib.b200_device_sync(self.dev.idx)
+                lib.b200_free_async(self.dev.idx, None, self.ptr)
             self.ptr = 0
 
     def __del__(self):

@@ -617,9 +617,11 @@ namespace alpaka
             return r;
         }
 
-        //! block scope for hierarchy::Threads / hierarchy::Blocks, device scope for hierarchy::Grids
+        //! CTA scope only for hierarchy::Threads (atomic between the threads of ONE block); hierarchy::Blocks means
+        //! "atomic between all blocks of a grid" and hierarchy::Grids "between grids", so both need device scope
+        //! (reference: atomic/AtomicUniformCudaHip.hpp:80-130 uses the *_block intrinsics for Threads only).
         template<typename THierarchy>
-        inline constexpr bool blockScope = !std::is_same_v<THierarchy, hierarchy::Grids>;
+        inline constexpr bool blockScope = std::is_same_v<THierarchy, hierarchy::Threads>;
 
         template<typename THierarchy, typename U>
         __device__ __forceinline__ auto cas(U* addr, U compare, U value) -> U

@@ -211,6 +211,105 @@ namespace alpaka::b200::native
         return WorkDivMembers<TDim, TIdx>{V::all(4), V::all(1024), V::all(1)};
     }
 
+    //! Cross-check of a functor claimed as the reference DotKernel (babelStreamMainTest.cpp:145-181): the user's functor
+    //! (generic trampoline, the caller's block size, 4 blocks) and the native single-pass kernel both reduce a small input
+    //! of small integers (every product and partial sum exact, so no summation order or FMA contraction can matter); the
+    //! native path is kept only if the two totals are identical. `generic(a, b, partials, n, blocks)` launches the user's
+    //! functor, `native(a, b, partials, n, blocks)` the library's; both fill `blocks` partials whose sum is the result.
+    template<typename TKernel, typename TAcc, typename T, typename TQueue, typename FGeneric, typename FNative>
+    auto verifyDot(TQueue& queue, FGeneric&& generic, FNative&& native) -> bool
+    {
+        auto& v = verdict<TKernel, TAcc, T>();
+        int const known = v.load(std::memory_order_acquire);
+        if(known != static_cast<int>(Verdict::Untested))
+            return known == static_cast<int>(Verdict::Native);
+
+        constexpr std::size_t n = 10007; // ragged: not a multiple of any block size
+        constexpr std::uint32_t blocks = 4;
+        int const dev = getDev(queue).getNativeHandle();
+        b200_stream_t const s = queue.getNativeHandle();
+        std::vector<T> h(2 * n);
+        for(std::size_t k = 0; k < 2 * n; ++k)
+            h[k] = static_cast<T>(static_cast<int>((k * 2654435761u >> 7) % 7u) - 3);
+        void* dIn = nullptr;
+        void* dOut = nullptr;
+        check(b200_malloc_async(dev, s, 2 * n * sizeof(T), &dIn));
+        check(b200_malloc_async(dev, s, 2 * blocks * sizeof(T), &dOut));
+        check(b200_memcpy_async(dev, dIn, h.data(), 2 * n * sizeof(T), B200_COPY_H2D, s));
+        check(b200_memset_async(dev, dOut, 0, 2 * blocks * sizeof(T), s));
+        T* in = static_cast<T*>(dIn);
+        T* out = static_cast<T*>(dOut);
+        generic(static_cast<T const*>(in), static_cast<T const*>(in + n), out, n, blocks);
+        native(static_cast<T const*>(in), static_cast<T const*>(in + n), out + blocks, n, blocks);
+        T res[2 * blocks];
+        check(b200_memcpy_async(dev, res, dOut, sizeof(res), B200_COPY_D2H, s));
+        check(b200_stream_sync(s));
+        check(b200_free_async(dev, s, dIn));
+        check(b200_free_async(dev, s, dOut));
+        T sumG{0}, sumN{0};
+        long long want = 0;
+        for(std::uint32_t k = 0; k < blocks; ++k)
+        {
+            sumG += res[k];
+            sumN += res[blocks + k];
+        }
+        for(std::size_t k = 0; k < n; ++k)
+            want += static_cast<long long>(h[k]) * static_cast<long long>(h[n + k]);
+        bool const same = sumG == sumN && sumN == static_cast<T>(want);
+        if(!same)
+            std::cerr << "[alpaka-b200] a kernel functor named DotKernel does not compute the reference's blockwise dot "
+                         "product; it keeps running through the generic trampoline"
+                      << std::endl;
+        v.store(static_cast<int>(same ? Verdict::Native : Verdict::Generic), std::memory_order_release);
+        return same;
+    }
+
+    //! Cross-check of a functor claimed as the reference ReduceKernel<B, T, Sum<T>> (example/reduce/src/kernel.hpp:42-132):
+    //! the user's functor (generic trampoline, the driver's two launches: G blocks, then one block over the partials) and the
+    //! native single-pass kernel reduce the same small-integer input; kept only if destination[0] is identical.
+    template<typename TKernel, typename TAcc, typename T, typename TQueue, typename FGeneric, typename FNative>
+    auto verifyReduce(TQueue& queue, FGeneric&& generic, FNative&& native) -> bool
+    {
+        auto& v = verdict<TKernel, TAcc, T>();
+        int const known = v.load(std::memory_order_acquire);
+        if(known != static_cast<int>(Verdict::Untested))
+            return known == static_cast<int>(Verdict::Native);
+
+        constexpr std::size_t n = 10007;
+        constexpr std::uint32_t blocks = 3;
+        int const dev = getDev(queue).getNativeHandle();
+        b200_stream_t const s = queue.getNativeHandle();
+        std::vector<T> h(n);
+        long long want = 0;
+        for(std::size_t k = 0; k < n; ++k)
+        {
+            int const x = static_cast<int>((k * 2654435761u >> 7) % 7u); // 0..6: exact in every element type
+            h[k] = static_cast<T>(x);
+            want += x;
+        }
+        void* dIn = nullptr;
+        void* dOut = nullptr;
+        check(b200_malloc_async(dev, s, n * sizeof(T), &dIn));
+        check(b200_malloc_async(dev, s, 2 * blocks * sizeof(T), &dOut));
+        check(b200_memcpy_async(dev, dIn, h.data(), n * sizeof(T), B200_COPY_H2D, s));
+        check(b200_memset_async(dev, dOut, 0, 2 * blocks * sizeof(T), s));
+        T* out = static_cast<T*>(dOut);
+        generic(static_cast<T const*>(dIn), out, n, blocks);
+        native(static_cast<T const*>(dIn), out + blocks, n);
+        T res[2 * blocks];
+        check(b200_memcpy_async(dev, res, dOut, sizeof(res), B200_COPY_D2H, s));
+        check(b200_stream_sync(s));
+        check(b200_free_async(dev, s, dIn));
+        check(b200_free_async(dev, s, dOut));
+        bool const same = res[0] == res[blocks] && res[blocks] == static_cast<T>(want);
+        if(!same)
+            std::cerr << "[alpaka-b200] a kernel functor named ReduceKernel<..., Sum<T>> does not compute the reference's "
+                         "sum; it keeps running through the generic trampoline"
+                      << std::endl;
+        v.store(static_cast<int>(same ? Verdict::Native : Verdict::Generic), std::memory_order_release);
+        return same;
+    }
+
     // ---- heatEquation2D plans: TMA descriptors + boundary tables per ping-pong buffer pair
     struct HeatPlanKey
     {
@@ -427,7 +526,7 @@ namespace alpaka::trait
     {
         static constexpr bool available = true;
         template<typename TQueue, typename TDim, typename TIdx, typename TK, typename TA, typename TB, typename T, typename TN>
-        static auto launch(TQueue& q, WorkDivMembers<TDim, TIdx> const& wd, TK const&, TA* a, TB* b, T* sum, TN arraySize)
+        static auto launch(TQueue& q, WorkDivMembers<TDim, TIdx> const& wd, TK const& k, TA* a, TB* b, T* sum, TN arraySize)
             -> std::enable_if_t<
                 std::is_same_v<std::remove_const_t<TA>, T> && std::is_same_v<std::remove_const_t<TB>, T> && std::is_integral_v<TN>,
                 bool>
@@ -439,6 +538,19 @@ namespace alpaka::trait
             {
                 auto const partials = static_cast<uint64_t>(wd.m_gridBlockExtent[0]);
                 if(partials < 2u || partials > 0xffffffffull)
+                    return false;
+                // claimed by NAME: cross-check once against the user's own functor (same block size, 4 blocks)
+                bool const ok = nv::verifyDot<TK, TAcc, T>(
+                    q,
+                    [&](T const* x, T const* y, T* out, std::size_t n, std::uint32_t blocks)
+                    {
+                        using V = Vec<TDim, TIdx>;
+                        WorkDivMembers<TDim, TIdx> const small{V::all(static_cast<TIdx>(blocks)), wd.m_blockThreadExtent, V::all(1)};
+                        b200::launchGeneric<TAcc>(q, small, k, static_cast<TA*>(const_cast<T*>(x)), static_cast<TB*>(const_cast<T*>(y)), out, static_cast<TN>(n));
+                    },
+                    [&](T const* x, T const* y, T* out, std::size_t n, std::uint32_t blocks)
+                    { b200::check(nv::dotPartials(q.getNativeHandle(), x, y, n, out, blocks, q.m_impl->reduceScratch())); });
+                if(!ok)
                     return false;
                 b200::check(nv::dotPartials(
                     q.getNativeHandle(),
@@ -458,7 +570,7 @@ namespace alpaka::trait
     // then one block  destination -> destination[0]. The reduction functor is an opaque type, so only
     // alpaka::b200::Sum<T> (the functor this library provides for "+") is claimed: the main launch becomes ONE
     // single-pass native reduction that leaves the total in destination[0] and zeros in destination[1..G); the
-    // second launch (source == destination) is then an identity and is skipped.
+    // second launch (source == destination) runs the same native kernel in place over those G values.
     template<std::uint32_t TBlockSize, typename T, typename TAcc>
     struct NativeKernel<::ReduceKernel<TBlockSize, T, b200::Sum<T>>, TAcc>
     {
@@ -467,21 +579,42 @@ namespace alpaka::trait
         static auto launch(
             TQueue& q,
             WorkDivMembers<TDim, TIdx> const& wd,
-            TK const&,
+            TK const& k,
             T const* source,
             T* destination,
             TN const& n,
-            b200::Sum<T> const&) -> std::enable_if_t<std::is_integral_v<TN>, bool>
+            b200::Sum<T> const& fn) -> std::enable_if_t<std::is_integral_v<TN>, bool>
         {
             namespace nv = b200::native;
             if constexpr(!nv::isReduceElem<T> || TDim::value != 1u)
                 return false;
             else
             {
-                if(source == destination)
-                    return true; // second launch of the pair: destination[0] already holds the total
-                auto const blocks = static_cast<std::size_t>(wd.m_gridBlockExtent[0]);
                 b200_stream_t const s = q.getNativeHandle();
+                // claimed by NAME: cross-check once against the user's own functor (the driver's two launches)
+                bool const ok = nv::verifyReduce<TK, TAcc, T>(
+                    q,
+                    [&](T const* in, T* out, std::size_t m, std::uint32_t blocks)
+                    {
+                        using V = Vec<TDim, TIdx>;
+                        WorkDivMembers<TDim, TIdx> const wd1{V::all(static_cast<TIdx>(blocks)), V::all(static_cast<TIdx>(TBlockSize)), V::all(1)};
+                        WorkDivMembers<TDim, TIdx> const wd2{V::all(1), V::all(static_cast<TIdx>(TBlockSize)), V::all(1)};
+                        b200::launchGeneric<TAcc>(q, wd1, k, in, out, static_cast<TN>(m), fn);
+                        b200::launchGeneric<TAcc>(q, wd2, k, static_cast<T const*>(out), out, static_cast<TN>(blocks), fn);
+                    },
+                    [&](T const* in, T* out, std::size_t m) { b200::check(nv::reduceSum(s, in, m, out, q.m_impl->reduceScratch())); });
+                if(!ok)
+                    return false;
+                if(source == destination)
+                {
+                    // In-place reduction of destination[0..n) into destination[0]: the second launch of the driver's pair
+                    // (after the native first launch it sums the total and G-1 zeros, x + 0 == x), or a stand-alone
+                    // in-place call -- never skipped, the kernel cannot know which. Safe in place: out[0] is written by the
+                    // last block after every block has finished reading (b200_reduce.cu, single-pass ticket).
+                    b200::check(nv::reduceSum(s, source, static_cast<uint64_t>(n), destination, q.m_impl->reduceScratch()));
+                    return true;
+                }
+                auto const blocks = static_cast<std::size_t>(wd.m_gridBlockExtent[0]);
                 int const dev = getDev(q).getNativeHandle();
                 if(blocks > 1u)
                     b200::check(b200_memset_async(dev, destination + 1, 0, (blocks - 1u) * sizeof(T), s));

@@ -127,7 +127,13 @@ def main():
             assert out.tobytes() == want_s.tobytes(), f"slab-decomposed {levels}-level heat differs from the undecomposed oracle"
         dist.barrier()
         slab.close()
+    # ---- every sharded path against the committed golden vectors of the UNMODIFIED reference (tests/golden_multi.py;
+    # the same block runs inside bench.py's N > 1 arm)
+    import golden_multi
+
+    verdict = golden_multi.check_all(golden_multi.Ranks(ab, world, {rank: q}, dist))
     if rank == 0:
+        print(f"MP_WORKER_GOLDEN {verdict}", flush=True)
         print(f"MP_WORKER_OK {world}", flush=True)
     dist.destroy_process_group()
 

@@ -63,6 +63,12 @@ def test_reference_babelstream_driver_unmodified(native):
     assert "AccGpuB200<1,unsigned int>" in r.stdout
 
 
+def test_block_hierarchy_atomics_are_atomic_between_blocks():
+    """4096 blocks x 256 threads add to ONE global counter under hierarchy::Blocks / Grids (tests/cpp/atomic_blocks.cpp)."""
+    r = run("test_atomic_blocks")
+    assert "-> OK" in r.stdout, r.stdout
+
+
 # Reference examples next to the hot path (SURVEY.md section 8f rows 2-3), compiled unmodified (examples/Makefile REFEX):
 # each is its own checker (exit status + the success line its main() prints).
 REF_EXAMPLES = {

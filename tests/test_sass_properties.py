@@ -72,3 +72,18 @@ def test_default_instantiations_do_not_spill(obj, needles):
         assert hits, f"no entry function matching {needle} in {obj}"
         for k, (stack, st, ld) in hits.items():
             assert (stack, st, ld) == (0, 0, 0), f"{k}: {stack} bytes stack, {st}/{ld} bytes spilled"
+
+
+def test_block_and_grid_hierarchy_atomics_have_device_scope():
+    """alpaka::hierarchy::Blocks means "atomic between all blocks of a grid" (reference: atomic/AtomicUniformCudaHip.hpp:80-130
+    uses the *_block intrinsics for hierarchy::Threads only): in tests/cpp/atomic_blocks.cpp every Blocks / Grids atomic must
+    compile to .GPU scope, and exactly the one hierarchy::Threads atomic to CTA scope (.SM)."""
+    path = os.path.join(ROOT, "build", "examples", "test_atomic_blocks")
+    if not os.path.exists(path) or not os.path.exists(CUOBJDUMP):
+        pytest.skip(f"{path} or cuobjdump missing")
+    text = subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True, check=True).stdout
+    atomics = re.findall(r"\b(?:ATOMG|REDG|ATOM|RED)\.[\w.]+", text)
+    gpu = [a for a in atomics if a.endswith(".GPU")]
+    cta = [a for a in atomics if a.endswith(".SM") or a.endswith(".CTA")]
+    assert len(gpu) >= 6, atomics      # u32 add x3, f64 add, max, cas
+    assert len(cta) == 1, atomics      # the single hierarchy::Threads add
