@@ -139,6 +139,7 @@ SIGNATURES: dict[str, list] = {
     "b200_ipc_event_open": [_i, C.c_char_p, _P(_vp)],
     "b200_func_attributes_get": [_i, _vp, _P(FuncAttributes)],
     "b200_launch": [_i, _vp, _P(_u32), _P(_u32), _sz, _vp, _P(_vp)],
+    "b200_mem_range": [_vp, _P(_vp), _P(_sz)],
     "b200_acc_dev_props_get": [_i, _i, _P(AccDevProps)],
     "b200_subdivide_grid_elems": [_i, _P(_u64), _P(_u64), _P(AccDevProps), _u64, _i, _i, _P(_u64), _P(_u64), _P(_u64)],
     "b200_is_valid_work_div": [_i, _P(_u64), _P(_u64), _P(_u64), _P(AccDevProps), _u64, _P(_i)],

@@ -728,6 +728,9 @@ namespace
         double lh, rh; // left neighbour's y*rX, right neighbour's x*rX
     };
 
+    // SQ: rX == rY bit for bit (square cells, dx == dy: every BASELINE.json heat configuration). Then v*rY IS v*rX -- the
+    // same IEEE product -- and one multiplication serves both directions: 2 multiplications + 4 additions per cell and level.
+    template<bool SQ>
     __device__ __forceinline__ RowN makeRowN(double x, double y, double rX, double rY)
     {
         RowN r;
@@ -735,8 +738,8 @@ namespace
         r.y = y;
         r.xh = __dmul_rn(x, rX);
         r.yh = __dmul_rn(y, rX);
-        r.xv = __dmul_rn(x, rY);
-        r.yv = __dmul_rn(y, rY);
+        r.xv = SQ ? r.xh : __dmul_rn(x, rY);
+        r.yv = SQ ? r.yh : __dmul_rn(y, rY);
         r.lh = r.rh = 0.0;
         return r;
     }
@@ -776,7 +779,7 @@ namespace
         return 0.0;
     }
 
-    template<int S, int RPT, int NWY, bool EDGE>
+    template<int S, int RPT, int NWY, bool EDGE, bool SQ>
     __device__ __forceinline__ void stepNRows(HeatNArgs const& A, double const* box, int32_t y0, int32_t x0, int wx, int wy, int lane)
     {
         using G = StepNGeom<S>;
@@ -793,11 +796,24 @@ namespace
         for(int i = 0; i < RPT + 2 * S; ++i)
         {
             // level 0, tile row r0 - S + i
-            double2 const a = lds128(p + size_t(i) * G::BOXX), b = lds128(p + size_t(i) * G::BOXX + 2),
-                          c = lds128(p + size_t(i) * G::BOXX + 4);
-            RowN N = makeRowN(b.x, b.y, A.rX, A.rY);
-            N.lh = __dmul_rn(a.y, A.rX);
-            N.rh = __dmul_rn(c.x, A.rX);
+            double2 const b = lds128(p + size_t(i) * G::BOXX + 2);
+            RowN N = makeRowN<SQ>(b.x, b.y, A.rX, A.rY);
+            if constexpr(S % 2 == 0)
+            {
+                // The neighbours' products come from the adjacent lanes, as at every other level: one LDS.128 per row and no
+                // extra multiplication. The window then loses one column per side at level 1 already, S columns in all --
+                // exactly the M = S columns an even S gives up anyway (lanes M/2 .. 31 - M/2 store).
+                N.lh = shflUp1(N.yh);
+                N.rh = shflDown1(N.xh);
+            }
+            else
+            {
+                // odd S: M = S - 1, the window cannot afford to lose a column at level 1; the cells left and right of the pair
+                // are read from the box (two 8-byte loads at a 16-byte lane stride: 2-way bank conflicts, ncu r02)
+                double2 const a = lds128(p + size_t(i) * G::BOXX), c = lds128(p + size_t(i) * G::BOXX + 4);
+                N.lh = __dmul_rn(a.y, A.rX);
+                N.rh = __dmul_rn(c.x, A.rX);
+            }
 #pragma unroll
             for(int l = 0; l < S; ++l)
             {
@@ -829,7 +845,7 @@ namespace
                         if(!(jDefined && gi + 1 >= 1 && gi + 1 <= int32_t(A.nx)))
                             vy = ringOrZeroN(A, gj, gi + 1, jLo, jHi, A.tf[l]);
                     }
-                    N = makeRowN(vx, vy, A.rX, A.rY);
+                    N = makeRowN<SQ>(vx, vy, A.rX, A.rY);
                     N.lh = shflUp1(N.yh);
                     N.rh = shflDown1(N.xh);
                 }
@@ -893,8 +909,10 @@ namespace
         }
     }
 
-    template<int S, int RPT, int NWY>
-    __global__ void __launch_bounds__(32 * StepNGeom<S>::NWX * NWY) heatStepNKernel(const __grid_constant__ CUtensorMap mapSrc, HeatNArgs const A)
+    template<int S, int RPT, int NWY, bool SQ, int MINB = 8 / NWY>
+    // minimum CTAs per SM pinned so that no variant exceeds 128 registers (4 CTAs of 128 threads / 2 of 256: what the
+    // 40 KB / 72 KB boxes admit anyway); MINB = 5 (heat.stepn_ctas = 5, square cells, default shape) trades 96 registers + a few spills for a fifth resident CTA
+    __global__ void __launch_bounds__(32 * StepNGeom<S>::NWX * NWY, MINB) heatStepNKernel(const __grid_constant__ CUtensorMap mapSrc, HeatNArgs const A)
     {
         using G = StepNGeom<S>;
         constexpr int TYT = NWY * RPT;
@@ -928,9 +946,9 @@ namespace
         bool const interior = !strip && y0 - (S - 1) >= A.loY && y0 + TYT + S - 2 <= A.hiY && x0 - G::M >= 1
                               && x0 + G::WOUT + G::M - 1 <= int32_t(A.nx);
         if(interior)
-            stepNRows<S, RPT, NWY, false>(A, box, y0, x0, wx, wy, lane);
+            stepNRows<S, RPT, NWY, false, SQ>(A, box, y0, x0, wx, wy, lane);
         else
-            stepNRows<S, RPT, NWY, true>(A, box, y0, x0, wx, wy, lane);
+            stepNRows<S, RPT, NWY, true, SQ>(A, box, y0, x0, wx, wy, lane);
 
         if(strip && A.stripCounter != nullptr)
         {
@@ -1132,12 +1150,19 @@ extern "C"
             optIn(heatStep2Kernel<1, 32, 32>, Step2Geom<32>::kBoxBytes);
             optIn(heatStep2Kernel<1, 64, 16>, Step2Geom<64>::kBoxBytes);
             optIn(heatStep2Kernel<1, 64, 32>, Step2Geom<64>::kBoxBytes);
-            optIn(heatStepNKernel<3, 16, 4>, StepNGeom<3>::BOXX * (64 + 6) * 8);
-            optIn(heatStepNKernel<3, 16, 2>, StepNGeom<3>::BOXX * (32 + 6) * 8);
-            optIn(heatStepNKernel<3, 32, 2>, StepNGeom<3>::BOXX * (64 + 6) * 8);
-            optIn(heatStepNKernel<4, 16, 4>, StepNGeom<4>::BOXX * (64 + 8) * 8);
-            optIn(heatStepNKernel<4, 16, 2>, StepNGeom<4>::BOXX * (32 + 8) * 8);
-            optIn(heatStepNKernel<4, 32, 2>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<3, 16, 4, false>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<3, 16, 4, true>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<3, 16, 2, false>, StepNGeom<3>::BOXX * (32 + 6) * 8);
+            optIn(heatStepNKernel<3, 16, 2, true>, StepNGeom<3>::BOXX * (32 + 6) * 8);
+            optIn(heatStepNKernel<3, 32, 2, false>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<3, 32, 2, true>, StepNGeom<3>::BOXX * (64 + 6) * 8);
+            optIn(heatStepNKernel<4, 16, 4, false>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<4, 16, 4, true>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<4, 16, 2, false>, StepNGeom<4>::BOXX * (32 + 8) * 8);
+            optIn(heatStepNKernel<4, 16, 2, true>, StepNGeom<4>::BOXX * (32 + 8) * 8);
+            optIn(heatStepNKernel<4, 16, 2, true, 5>, StepNGeom<4>::BOXX * (32 + 8) * 8);
+            optIn(heatStepNKernel<4, 32, 2, false>, StepNGeom<4>::BOXX * (64 + 8) * 8);
+            optIn(heatStepNKernel<4, 32, 2, true>, StepNGeom<4>::BOXX * (64 + 8) * 8);
             if(e != cudaSuccess)
             {
                 cudaFree(plan->sx);
@@ -1387,7 +1412,7 @@ extern "C"
                 A.myFlags = plan->halo.my_flags;
                 A.stripCounter = plan->haloScratch;
                 A.status = plan->haloScratch + 1;
-        A.waitNs = b200::waitLimitNs();
+                A.waitNs = b200::waitLimitNs();
                 A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
                 A.step = haloStep;
                 // heat.halo_debug (measurement only, results become wrong): 1 = no peer stores, 2 = no flag wait
@@ -1501,7 +1526,7 @@ extern "C"
                 A.myFlags = plan->halo.my_flags;
                 A.stripCounter = plan->haloScratch;
                 A.status = plan->haloScratch + 1;
-        A.waitNs = b200::waitLimitNs();
+                A.waitNs = b200::waitLimitNs();
                 A.stripTiles = (A.nTop + A.nBot) * A.tilesX;
                 A.step = haloStep;
                 int64_t const dbg = b200::tune("heat.halo_debug", 0);
@@ -1515,25 +1540,37 @@ extern "C"
             auto const s = reinterpret_cast<cudaStream_t>(stream);
             size_t const smemBytes = size_t(boxX) * size_t(tyt + 2 * levels) * 8;
             auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->mapN[src_index], A); };
+            // square cells (dx == dy): rX == rY bit for bit, one product serves both directions (makeRowN<SQ>)
+            bool const sq = rx == ry && b200::tune("heat.stepn_sq", 1) != 0;
+            auto go = [&]<int S_, int RPT_, int NWY_>(int threads)
+            {
+                if(sq)
+                    launch(heatStepNKernel<S_, RPT_, NWY_, true>, threads);
+                else
+                    launch(heatStepNKernel<S_, RPT_, NWY_, false>, threads);
+            };
             switch(levels * 10000 + rpt * 100 + nwy)
             {
             case 31604:
-                launch(heatStepNKernel<3, 16, 4>, 256);
+                go.template operator()<3, 16, 4>(256);
                 break;
             case 31602:
-                launch(heatStepNKernel<3, 16, 2>, 128);
+                go.template operator()<3, 16, 2>(128);
                 break;
             case 33202:
-                launch(heatStepNKernel<3, 32, 2>, 128);
+                go.template operator()<3, 32, 2>(128);
                 break;
             case 41604:
-                launch(heatStepNKernel<4, 16, 4>, 256);
+                go.template operator()<4, 16, 4>(256);
                 break;
             case 41602:
-                launch(heatStepNKernel<4, 16, 2>, 128);
+                if(sq && b200::tune("heat.stepn_ctas", 4) == 5)
+                    launch(heatStepNKernel<4, 16, 2, true, 5>, 128);
+                else
+                    go.template operator()<4, 16, 2>(128);
                 break;
             case 43202:
-                launch(heatStepNKernel<4, 32, 2>, 128);
+                go.template operator()<4, 32, 2>(128);
                 break;
             default:
                 return b200::fail(B200_EINVAL, "heat.stepn_rpt/heat.stepn_nwy: supported 16/2, 16/4, 32/2", __FILE__, __LINE__);

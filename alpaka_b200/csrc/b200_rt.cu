@@ -159,6 +159,33 @@ namespace b200
 
 using namespace b200;
 
+namespace
+{
+    // ---- registry of the device allocations this library handed out: base -> size. The generic launch path asks it whether
+    // the pointer arguments of a kernel lie in pairwise distinct allocations (then no in-bounds access through one can alias
+    // an access through another, and the kernel may be compiled with restrict-qualified parameters; Kernel.hpp).
+    std::mutex g_allocMutex;
+    std::map<uintptr_t, size_t>& allocMap()
+    {
+        static std::map<uintptr_t, size_t> m;
+        return m;
+    }
+
+    void registerAlloc(void* p, size_t bytes)
+    {
+        if(p == nullptr)
+            return;
+        std::lock_guard<std::mutex> l(g_allocMutex);
+        allocMap()[reinterpret_cast<uintptr_t>(p)] = bytes;
+    }
+
+    void unregisterAlloc(void* p)
+    {
+        std::lock_guard<std::mutex> l(g_allocMutex);
+        allocMap().erase(reinterpret_cast<uintptr_t>(p));
+    }
+} // namespace
+
 extern "C"
 {
     int b200_abi_version(void)
@@ -472,6 +499,7 @@ extern "C"
         if(bytes == 0)
             return 0; // zero-sized buffers are legal (test/unit/mem/buf BufTest "zero-size")
         B200_CUDA(cudaMallocAsync(out, bytes, cs(s)));
+        registerAlloc(*out, bytes);
         return 0;
     }
 
@@ -480,6 +508,7 @@ extern "C"
         if(!ptr)
             return 0;
         B200_CUDA(cudaSetDevice(dev));
+        unregisterAlloc(ptr);
         B200_CUDA(cudaFreeAsync(ptr, cs(s)));
         return 0;
     }
@@ -500,6 +529,7 @@ extern "C"
         if(bytes == 0)
             return 0;
         B200_CUDA(cudaMalloc(out, bytes));
+        registerAlloc(*out, bytes);
         return 0;
     }
 
@@ -508,7 +538,30 @@ extern "C"
         if(!ptr)
             return 0;
         B200_CUDA(cudaSetDevice(dev));
+        unregisterAlloc(ptr);
         B200_CUDA(cudaFree(ptr));
+        return 0;
+    }
+
+    int b200_mem_range(void const* ptr, void** base, size_t* bytes)
+    {
+        B200_REQUIRE(base && bytes, B200_EINVAL);
+        *base = nullptr;
+        *bytes = 0;
+        if(ptr == nullptr)
+            return 0;
+        auto const a = reinterpret_cast<uintptr_t>(ptr);
+        std::lock_guard<std::mutex> l(g_allocMutex);
+        auto& m = allocMap();
+        auto it = m.upper_bound(a);
+        if(it == m.begin())
+            return 0;
+        --it;
+        if(a < it->first + it->second)
+        {
+            *base = reinterpret_cast<void*>(it->first);
+            *bytes = it->second;
+        }
         return 0;
     }
 

@@ -8,7 +8,10 @@
 //     all loads of an iteration issued before the first store;
 //   * a block owns a contiguous chunk of blockDim*UNROLL vectors per iteration, a warp access is one
 //     contiguous 512 B / 1 KiB span (fully coalesced, 4 or 8 sectors per request per thread);
-//   * grid: ONE block per chunk by default (stream.ctas_per_sm = 0). Measured on B200 at 2^30 doubles
+//   * grid: ONE block per chunk by default (stream.ctas_per_sm = 0); chunk = 1024 vectors (32 KB per array) for the
+//     operations that load (round 2: tools/stream_lab.cu -- launch shape x cache policy x 1-D bulk-copy staging through
+//     shared memory x array placement; nothing but the chunk size moves the mixed read/write figure, which sits at
+//     7.1 TB/s against 7.55 TB/s for loads alone and 7.60 TB/s for stores alone). Measured on B200 at 2^30 doubles
 //     (tools/tune.py stream, profiles/r01/tune_stream.log): one-chunk blocks reach 7.0-7.1 TB/s for Copy/Mul/Triad and
 //     7.6 TB/s for Init, a persistent grid of SMs x {2,4,8} blocks striding over the chunks only 6.1-6.7 TB/s -- the
 //     hardware block scheduler spreads the DRAM pages touched at any instant better than lock-step strides do;
@@ -294,8 +297,11 @@ namespace
     };
 
     // ---- the kernel: persistent (or one-chunk-per-block) grid-stride over chunks of blockDim*UNROLL vectors
+    template<int UNROLL>
+    inline constexpr int kMaxBlock = UNROLL == 1 ? 1024 : 512;
+
     template<typename Op, typename T, int VB, int UNROLL, int HINT>
-    __global__ void __launch_bounds__(512) streamKernel(Op const op, uint64_t const nVec, uint64_t const n)
+    __global__ void __launch_bounds__(kMaxBlock<UNROLL>) streamKernel(Op const op, uint64_t const nVec, uint64_t const n)
     {
         using In = typename Op::template In<VB>;
         uint64_t const chunk = uint64_t(blockDim.x) * UNROLL;
@@ -341,15 +347,36 @@ namespace
         int vb, unroll, hint, block, ctasPerSm;
     };
 
+    // Launch shape per operation, measured on B200 at 2^30 doubles (tools/stream_lab.cu, profiles/r02/tune_stream_*.log;
+    // reproducible to 1 GB/s): a CTA that owns 32 KB of every array beats the 16 KB one of round 1 --
+    //   Triad (two loads in flight per vector)  1024 threads x 1 vector   7130 vs 7089 GB/s
+    //   Copy  (one load per vector)              256 threads x 4 vectors  7098 vs 6994 GB/s
+    // Add follows Triad, Mul follows Copy; Init (stores only, 7.59 TB/s) and Nstream keep 512 x 1.
+    struct ShapeDefault
+    {
+        int unroll, block;
+    };
+
+    ShapeDefault shapeDefault(char const* opName)
+    {
+        std::string const op(opName);
+        if(op == "triad" || op == "add")
+            return {1, 1024};
+        if(op == "copy" || op == "mul")
+            return {4, 256};
+        return {1, 512};
+    }
+
     StreamCfg streamCfg(char const* opName, int elemBytes)
     {
         (void) elemBytes;
         StreamCfg c;
         std::string const p = std::string("stream.") + opName + ".";
+        ShapeDefault const d = shapeDefault(opName);
         c.vb = int(b200::tune((p + "vb").c_str(), b200::tune("stream.vb", 32)));
-        c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", 1)));
+        c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", d.unroll)));
         c.hint = int(b200::tune((p + "hint").c_str(), b200::tune("stream.hint", 1)));
-        c.block = int(b200::tune((p + "block").c_str(), b200::tune("stream.block", 512)));
+        c.block = int(b200::tune((p + "block").c_str(), b200::tune("stream.block", d.block)));
         c.ctasPerSm = int(b200::tune((p + "ctas_per_sm").c_str(), b200::tune("stream.ctas_per_sm", 0)));
         return c;
     }
@@ -397,8 +424,8 @@ namespace
             return 0;
         auto const s = reinterpret_cast<cudaStream_t>(stream);
         StreamCfg cfg = streamCfg(name, int(sizeof(T)));
-        if(cfg.block < 32 || cfg.block > 512 || cfg.block % 32 != 0)
-            return b200::fail(B200_EINVAL, "stream.block must be a multiple of 32 in [32,512]", __FILE__, __LINE__);
+        if(cfg.block < 32 || cfg.block % 32 != 0 || cfg.block > (cfg.unroll == 1 ? 1024 : 512))
+            return b200::fail(B200_EINVAL, "stream.block must be a multiple of 32 in [32,1024] (<= 512 when stream.unroll > 1)", __FILE__, __LINE__);
         int vb = cfg.vb;
         if(vb == 32 && !aligned32)
             vb = 16;

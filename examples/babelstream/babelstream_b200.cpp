@@ -25,6 +25,18 @@
 #include <string>
 #include <vector>
 
+#ifdef BABELSTREAM_RENAMED_FUNCTORS
+// The same functors under names the library has never heard of (build/examples/babelstream_b200_renamed): nothing is
+// recognised, every launch takes the GENERIC path -- the block-coarsened trampoline where the launch proves it safe.
+#    define InitKernel UserInit
+#    define CopyKernel UserCopy
+#    define MultKernel UserScale
+#    define AddKernel UserSum
+#    define TriadKernel UserTriad
+#    define NstreamKernel UserNstream
+#    define DotKernel UserDot
+#endif
+
 constexpr double scalarVal = 2.0;
 constexpr double valA = 1.0;
 constexpr unsigned dotBlockThreads = 1024;

@@ -34,6 +34,15 @@ namespace alpaka
     };
     using ApiCudaRt = ApiB200Rt;
 
+#if defined(__CUDACC__)
+    namespace b200
+    {
+        //! dim3-like built-in -> alpaka vector (defined with the device-side traits below)
+        template<typename TDim, typename TIdx, typename TBuiltin>
+        __device__ __forceinline__ auto fromBuiltin(TBuiltin const& v) -> Vec<TDim, TIdx>;
+    } // namespace b200
+#endif
+
     //! The B200 accelerator. Constructed on the device by the kernel trampoline; never copied.
     template<typename TApi, typename TDim, typename TIdx>
     class AccGpuUniformCudaHipRt final
@@ -42,8 +51,24 @@ namespace alpaka
         static_assert(TDim::value <= 3u, "The B200 accelerator supports 0 to 3 dimensions (CUDA grids are 3-D).");
 
     public:
+        //! the launch as the hardware sees it: grid extent and block index are CUDA's built-ins
         ALPAKA_FN_HOST_ACC explicit AccGpuUniformCudaHipRt(Vec<TDim, TIdx> const& threadElemExtent)
             : m_threadElemExtent(threadElemExtent)
+#if defined(__CUDA_ARCH__)
+            , m_gridBlockExtent(b200::fromBuiltin<TDim, TIdx>(gridDim))
+            , m_blockIdx(b200::fromBuiltin<TDim, TIdx>(blockIdx))
+#endif
+        {
+        }
+        //! a VIRTUAL block of the user's grid executed by a physical block of a coarsened launch (b200k::runCoarse):
+        //! getWorkDiv<Grid, Blocks> and getIdx<Grid, Blocks> answer with the user's grid, not the hardware's
+        ALPAKA_FN_HOST_ACC AccGpuUniformCudaHipRt(
+            Vec<TDim, TIdx> const& threadElemExtent,
+            Vec<TDim, TIdx> const& gridBlockExtent,
+            Vec<TDim, TIdx> const& blockIdxInGrid)
+            : m_threadElemExtent(threadElemExtent)
+            , m_gridBlockExtent(gridBlockExtent)
+            , m_blockIdx(blockIdxInGrid)
         {
         }
         AccGpuUniformCudaHipRt(AccGpuUniformCudaHipRt const&) = delete;
@@ -52,6 +77,8 @@ namespace alpaka
         auto operator=(AccGpuUniformCudaHipRt&&) -> AccGpuUniformCudaHipRt& = delete;
 
         Vec<TDim, TIdx> const& m_threadElemExtent;
+        Vec<TDim, TIdx> const m_gridBlockExtent{};
+        Vec<TDim, TIdx> const m_blockIdx{};
     };
 
     template<typename TDim, typename TIdx>
@@ -421,9 +448,9 @@ namespace alpaka
         template<typename TApi, typename TDim, typename TIdx>
         struct GetWorkDiv<AccGpuUniformCudaHipRt<TApi, TDim, TIdx>, origin::Grid, unit::Blocks>
         {
-            __device__ static auto getWorkDiv(AccGpuUniformCudaHipRt<TApi, TDim, TIdx> const&) -> Vec<TDim, TIdx>
+            __device__ static auto getWorkDiv(AccGpuUniformCudaHipRt<TApi, TDim, TIdx> const& acc) -> Vec<TDim, TIdx>
             {
-                return b200::fromBuiltin<TDim, TIdx>(gridDim);
+                return acc.m_gridBlockExtent;
             }
         };
         template<typename TApi, typename TDim, typename TIdx>
@@ -450,9 +477,9 @@ namespace alpaka
         struct GetIdx<AccGpuUniformCudaHipRt<TApi, TDim, TIdx>, origin::Grid, unit::Blocks>
         {
             template<typename TWorkDiv>
-            __device__ static auto getIdx(AccGpuUniformCudaHipRt<TApi, TDim, TIdx> const&, TWorkDiv const&) -> Vec<TDim, TIdx>
+            __device__ static auto getIdx(AccGpuUniformCudaHipRt<TApi, TDim, TIdx> const& acc, TWorkDiv const&) -> Vec<TDim, TIdx>
             {
-                return b200::fromBuiltin<TDim, TIdx>(blockIdx);
+                return acc.m_blockIdx;
             }
         };
         template<typename TApi, typename TDim, typename TIdx>

@@ -19,8 +19,11 @@
 #include "Acc.hpp"
 
 #include <cstdlib>
+#include <map>
+#include <mutex>
 #include <tuple>
 #include <type_traits>
+#include <utility>
 
 namespace alpaka
 {
@@ -134,10 +137,154 @@ namespace alpaka
             TAcc const acc(threadElemExtent);
             kernelFnObj(acc, args...);
         }
+
+        //! pointer parameters of the coarsened trampoline are restrict-qualified (the launch proved they cannot alias)
+        template<typename T>
+        struct NoAlias
+        {
+            using type = T;
+        };
+        template<typename T>
+        struct NoAlias<T*>
+        {
+            using type = T* __restrict__;
+        };
+
+        //! The BLOCK-COARSENED trampoline. One-element-per-thread functors (the reference's contract,
+        //! kernel/TaskKernelGpuUniformCudaHipRt.hpp:61-76) keep 8 bytes per load in flight per thread: 16 KB per SM, about
+        //! 60 % of the HBM bandwidth of a B200 whatever the block size. Here a physical block runs V consecutive VIRTUAL
+        //! blocks of the user's grid (fastest dimension) one after the other, unrolled; the accelerator object answers
+        //! getIdx / getWorkDiv with the user's grid. Blocks are independent by the programming model, so this is the
+        //! same program; because the launch site has PROVEN that the pointer arguments lie in pairwise distinct
+        //! allocations (b200_mem_range) they are restrict-qualified, and the compiler hoists the loads of all V virtual
+        //! blocks above the first store: V times the bytes in flight with the user's functor unchanged.
+        //! Only launched for functors without shared memory (nothing to protect between virtual blocks).
+        //! TArgs arrive ALREADY restrict-qualified (the launch site instantiates with NoAlias<T>::type...): nvcc honours
+        //! restrict on the parameters of a __global__ function only -- measured, tools/README.md -- and a pack of dependent
+        //! parameter types does not survive its host stub, so the qualifier travels inside the template arguments.
+        template<int V, typename TKernelFnObj, typename TAcc, typename TDim, typename TIdx, typename... TArgs>
+        __global__ void runCoarse(
+            Vec<TDim, TIdx> const threadElemExtent,
+            Vec<TDim, TIdx> const gridBlockExtent,
+            TKernelFnObj const kernelFnObj,
+            TArgs... args)
+        {
+            constexpr std::size_t x = TDim::value - 1u; // alpaka's last component is CUDA's x
+            Vec<TDim, TIdx> block = alpaka::b200::fromBuiltin<TDim, TIdx>(blockIdx);
+            TIdx const first = block[x] * static_cast<TIdx>(V);
+            if(first + static_cast<TIdx>(V) <= gridBlockExtent[x])
+            {
+#    pragma unroll
+                for(int v = 0; v < V; ++v)
+                {
+                    block[x] = first + static_cast<TIdx>(v);
+                    TAcc const acc(threadElemExtent, gridBlockExtent, block);
+                    kernelFnObj(acc, args...);
+                }
+            }
+            else
+            {
+                for(TIdx b = first; b < gridBlockExtent[x]; ++b)
+                {
+                    block[x] = b;
+                    TAcc const acc(threadElemExtent, gridBlockExtent, block);
+                    kernelFnObj(acc, args...);
+                }
+            }
+        }
     } // namespace b200k
 #endif
 
 #if defined(__CUDACC__)
+    namespace b200::detail
+    {
+        //! Arguments through which no hidden pointer can reach the kernel: raw pointers (checked at the launch),
+        //! arithmetic / enum values and alpaka vectors of them. Anything else (a view object, a struct with pointer
+        //! members) keeps the plain trampoline. The functor itself must be stateless for the same reason.
+        template<typename T>
+        inline constexpr bool plainValueArg = std::is_arithmetic_v<T> || std::is_enum_v<T>;
+        template<typename TDim, typename TVal>
+        inline constexpr bool plainValueArg<Vec<TDim, TVal>> = std::is_arithmetic_v<TVal>;
+        template<typename T>
+        inline constexpr bool coarsenableArg
+            = plainValueArg<std::remove_cv_t<T>>
+              || (std::is_pointer_v<T> && (std::is_arithmetic_v<std::remove_cv_t<std::remove_pointer_t<T>>>) );
+        template<typename TKernelFnObj, typename... TArgs>
+        inline constexpr bool coarsenable = std::is_empty_v<TKernelFnObj> && (coarsenableArg<TArgs> && ...)
+                                            && (std::is_pointer_v<TArgs> || ...);
+
+        //! tunable `generic.coarsen` (B200_TUNE / b200_tune_set): 4 (default) or 0 = always the plain trampoline
+        inline auto coarsenFactor() -> int
+        {
+            int64_t v = 4;
+            (void) b200_tune_get("generic.coarsen", &v);
+            return static_cast<int>(v);
+        }
+
+        //! coarsen only grids that still fill the device afterwards: >= 32 virtual blocks per SM along x
+        template<typename TDev>
+        auto coarsenMinBlocks(TDev const& dev) -> std::uint64_t
+        {
+            static std::uint64_t const n = [&]
+            {
+                b200_device_props p{};
+                return b200_device_props_get(dev.getNativeHandle(), &p) == 0 ? static_cast<std::uint64_t>(p.multi_processor_count) * 32u
+                                                                            : std::uint64_t{148u * 32u};
+            }();
+            return n;
+        }
+
+        struct PtrArg
+        {
+            void const* p;
+            bool writable;
+        };
+
+        //! true iff every pointer argument lies in an allocation of this library and no WRITABLE pointer shares its
+        //! allocation with any other pointer argument (two read-only pointers may: nothing is modified through them)
+        template<typename... TArgs>
+        auto argsCannotAlias(TArgs const&... args) -> bool
+        {
+            PtrArg ptrs[sizeof...(TArgs) + 1u];
+            std::size_t n = 0;
+            auto const collect = [&](auto const& a)
+            {
+                using A = std::decay_t<decltype(a)>;
+                if constexpr(std::is_pointer_v<A>)
+                    ptrs[n++] = PtrArg{static_cast<void const*>(a), !std::is_const_v<std::remove_pointer_t<A>>};
+            };
+            (collect(args), ...);
+            void* base[sizeof...(TArgs) + 1u];
+            for(std::size_t i = 0; i < n; ++i)
+            {
+                std::size_t bytes = 0;
+                if(b200_mem_range(ptrs[i].p, &base[i], &bytes) != 0 || base[i] == nullptr)
+                    return false; // foreign memory: nothing is known about it
+            }
+            for(std::size_t i = 0; i < n; ++i)
+                for(std::size_t j = i + 1; j < n; ++j)
+                    if(base[i] == base[j] && (ptrs[i].writable || ptrs[j].writable))
+                        return false;
+            return true;
+        }
+
+        //! the coarsened instantiation holds no static shared memory (cached per kernel and device)
+        inline auto usesNoSharedMemory(int dev, void const* kernel) -> bool
+        {
+            static std::mutex mutex;
+            static std::map<std::pair<int, void const*>, bool> cache;
+            std::lock_guard<std::mutex> l(mutex);
+            auto const key = std::make_pair(dev, kernel);
+            auto const it = cache.find(key);
+            if(it != cache.end())
+                return it->second;
+            b200_func_attributes a{};
+            bool const ok = b200_func_attributes_get(dev, kernel, &a) == 0 && a.shared_size_bytes == 0u;
+            cache.emplace(key, ok);
+            return ok;
+        }
+    } // namespace b200::detail
+
     namespace b200
     {
         //! Launches `kernelFnObj(acc, args...)` through the generic trampoline on the queue's stream (no
@@ -171,6 +318,39 @@ namespace alpaka
 #    endif
             std::size_t const dynSmemBytes
                 = getBlockSharedMemDynSizeBytes<TAcc>(kernelFnObj, blockThreadExtent, threadElemExtent, args...);
+
+            // block-coarsened, restrict-qualified trampoline when it is provably the same program (see b200k::runCoarse)
+            if constexpr(TDim::value >= 1u && detail::coarsenable<TKernelFnObj, TArgs...>)
+            {
+                constexpr int V = 4;
+                if(dynSmemBytes == 0u && detail::coarsenFactor() == V
+                   && static_cast<std::uint64_t>(gridBlockExtent[TDim::value - 1u]) >= detail::coarsenMinBlocks(getDev(queue))
+                   && detail::argsCannotAlias(args...))
+                {
+                    void const* const coarse = (void const*) b200k::runCoarse<V, TKernelFnObj, TAcc, TDim, TIdx, typename b200k::NoAlias<TArgs>::type...>;
+                    if(detail::usesNoSharedMemory(getDev(queue).getNativeHandle(), coarse))
+                    {
+                        grid[0] = (grid[0] + static_cast<uint32_t>(V) - 1u) / static_cast<uint32_t>(V);
+                        void* argvCoarse[3u + sizeof...(TArgs)]
+                            = {const_cast<void*>(static_cast<void const*>(&threadElemExtent)),
+                               const_cast<void*>(static_cast<void const*>(&gridBlockExtent)),
+                               const_cast<void*>(static_cast<void const*>(&kernelFnObj)),
+                               const_cast<void*>(static_cast<void const*>(&args))...};
+                        check(b200_launch(
+                            getDev(queue).getNativeHandle(),
+                            coarse,
+                            grid,
+                            block,
+                            0u,
+                            queue.getNativeHandle(),
+                            argvCoarse));
+#    if ALPAKA_DEBUG >= ALPAKA_DEBUG_MINIMAL
+                        check(b200_stream_sync(queue.getNativeHandle()));
+#    endif
+                        return;
+                    }
+                }
+            }
 
             auto const kernel = b200k::run<TKernelFnObj, TAcc, TDim, TIdx, TArgs...>;
 

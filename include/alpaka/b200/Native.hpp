@@ -575,15 +575,15 @@ namespace alpaka::trait
     struct NativeKernel<::ReduceKernel<TBlockSize, T, b200::Sum<T>>, TAcc>
     {
         static constexpr bool available = true;
-        template<typename TQueue, typename TDim, typename TIdx, typename TK, typename TN>
+        template<typename TQueue, typename TDim, typename TIdx, typename TK, typename TSrc, typename TN>
         static auto launch(
             TQueue& q,
             WorkDivMembers<TDim, TIdx> const& wd,
             TK const& k,
-            T const* source,
+            TSrc* source,
             T* destination,
             TN const& n,
-            b200::Sum<T> const& fn) -> std::enable_if_t<std::is_integral_v<TN>, bool>
+            b200::Sum<T> const& fn) -> std::enable_if_t<std::is_integral_v<TN> && std::is_same_v<std::remove_const_t<TSrc>, T>, bool>
         {
             namespace nv = b200::native;
             if constexpr(!nv::isReduceElem<T> || TDim::value != 1u)
@@ -599,8 +599,10 @@ namespace alpaka::trait
                         using V = Vec<TDim, TIdx>;
                         WorkDivMembers<TDim, TIdx> const wd1{V::all(static_cast<TIdx>(blocks)), V::all(static_cast<TIdx>(TBlockSize)), V::all(1)};
                         WorkDivMembers<TDim, TIdx> const wd2{V::all(1), V::all(static_cast<TIdx>(TBlockSize)), V::all(1)};
-                        b200::launchGeneric<TAcc>(q, wd1, k, in, out, static_cast<TN>(m), fn);
-                        b200::launchGeneric<TAcc>(q, wd2, k, static_cast<T const*>(out), out, static_cast<TN>(blocks), fn);
+                        // exactly the argument types of THIS launch: the trampoline instantiation that is its generic
+                        // fall-back anyway (nvcc does not emit a kernel first instantiated inside a lambda of a template)
+                        b200::launchGeneric<TAcc>(q, wd1, k, static_cast<TSrc*>(const_cast<T*>(in)), out, static_cast<TN>(m), fn);
+                        b200::launchGeneric<TAcc>(q, wd2, k, static_cast<TSrc*>(out), out, static_cast<TN>(blocks), fn);
                     },
                     [&](T const* in, T* out, std::size_t m) { b200::check(nv::reduceSum(s, in, m, out, q.m_impl->reduceScratch())); });
                 if(!ok)

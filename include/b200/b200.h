@@ -159,6 +159,12 @@ extern "C"
         int32_t ptx_version, binary_version;
     } b200_func_attributes;
     int b200_func_attributes_get(int dev, void const* func, b200_func_attributes* out);
+    /* The device allocation of THIS library (b200_malloc_async / b200_malloc_pitched_async / b200_malloc_device) that
+     * contains `ptr`: *base / *bytes, or *base = NULL when the pointer is foreign. New: the generic launch path uses it to
+     * prove that a kernel's pointer arguments cannot alias (pairwise distinct allocations) before it picks the
+     * restrict-qualified, block-coarsened trampoline (include/alpaka/b200/Kernel.hpp); the reference has no counterpart
+     * (kernel/TaskKernelGpuUniformCudaHipRt.hpp:61-76 always runs one element per thread). */
+    int b200_mem_range(void const* ptr, void** base, size_t* bytes);
     int b200_launch(int dev, void const* func, uint32_t const grid[3], uint32_t const block[3], size_t dyn_smem_bytes, b200_stream_t s, void** args);
     /* Device address of a __device__ / __constant__ variable registered with the shared cudart instance
      * (replaces ApiCudaRt::getSymbolAddress, core/ApiCudaRt.hpp, as used by the device-global copies in

@@ -87,6 +87,30 @@ def test_heat2d_n_level_kernel_every_tile_shape(gpu, cfg):
     assert got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("variant", [{}, {"heat.stepn_sq": 0}, {"heat.stepn_ctas": 5}, {"heat.stepn_rpt": 32}, {"heat.stepn_nwy": 4}],
+                         ids=lambda v: "default" if not v else "_".join(f"{k.split('.')[1]}{x}" for k, x in v.items()))
+@pytest.mark.parametrize("levels", [3, 4])
+def test_heat2d_n_level_kernel_square_cells(gpu, levels, variant):
+    """Square cells (ny == nx -> rX == rY bit for bit): the N-level kernel shares ONE product v*rX between the horizontal
+    and the vertical terms (makeRowN<SQ>). Rough field, partial tiles on both axes; the shared-product kernel, the general
+    kernel forced on the same field (heat.stepn_sq = 0) and the five-CTA build must all equal the oracle bit for bit."""
+    ab, dev, queue = gpu
+    ny = nx = 333
+    dx, dy, dt = ol.heat_params(ny, nx)
+    assert dt / (dx * dx) == dt / (dy * dy)
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=23).reshape(ny + 2, nx + 2)
+    steps = 2 * levels + 1
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    for k, v in variant.items():
+        ab.runtime.tune_set(k, v)
+    try:
+        got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
+    finally:
+        for k, v in {"heat.stepn_sq": 1, "heat.stepn_ctas": 4, "heat.stepn_rpt": 16, "heat.stepn_nwy": 2}.items():
+            ab.runtime.tune_set(k, v)
+    assert got.tobytes() == want.tobytes()
+
+
 def test_heat2d_two_step_refuses_decomposed_tiles(gpu):
     """Ghost sides would need the neighbour's intermediate level: the C ABI refuses instead of computing garbage."""
     ab, dev, queue = gpu

@@ -120,7 +120,8 @@ def run_slabs(ab, dev, NY, NX, world, steps, u0, levels):
 
 # (world, rows per slab, NX): slabs smaller than one 64-row tile (everything is a strip), a slab whose last two core
 # rows straddle two tile rows (ny = 127), slabs with interior tile rows and partial tiles in x, a single slab
-SLAB_CASES = [(2, 20, 96), (3, 61, 200), (2, 127, 391), (4, 200, 700), (1, 150, 300), (8, 64, 256)]
+SLAB_CASES = [(2, 20, 96), (3, 61, 200), (2, 127, 391), (4, 200, 700), (1, 150, 300), (8, 64, 256),
+              (2, 128, 256), (4, 75, 300)]  # the last two: square cells (NY == NX), the shared-product kernel
 
 
 @pytest.mark.parametrize("levels", [2, 3, 4])

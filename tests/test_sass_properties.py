@@ -62,8 +62,8 @@ def ptxas_entries(name):
 @pytest.mark.parametrize("obj,needles", [
     ("b200_stream", ["TriadOpIdEEdLi32ELi1ELi1E", "CopyOpIdEEdLi32ELi1ELi1E", "NstreamOpIdEEdLi32ELi1ELi1E"]),
     ("b200_reduce", ["reduceKernelIdLb1ELi2E", "reduceKernelIjLb0ELi4E", "reduceKernelIfLb0ELi4E"]),
-    ("b200_heat2d", ["heatStepKernelILi1ELi8E", "heatStep2KernelILi1ELi64ELi16E", "heatStepNKernelILi4ELi16ELi2E",
-                     "heatStepNKernelILi3ELi16ELi2E"]),
+    ("b200_heat2d", ["heatStepKernelILi1ELi8E", "heatStep2KernelILi1ELi64ELi16E", "heatStepNKernelILi4ELi16ELi2ELb1ELi4E", "heatStepNKernelILi4ELi16ELi2ELb0ELi4E",
+                     "heatStepNKernelILi3ELi16ELi2ELb1ELi4E"]),
 ])
 def test_default_instantiations_do_not_spill(obj, needles):
     entries = ptxas_entries(obj)
@@ -82,8 +82,18 @@ def test_block_and_grid_hierarchy_atomics_have_device_scope():
     if not os.path.exists(path) or not os.path.exists(CUOBJDUMP):
         pytest.skip(f"{path} or cuobjdump missing")
     text = subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True, check=True).stdout
-    atomics = re.findall(r"\b(?:ATOMG|REDG|ATOM|RED)\.[\w.]+", text)
-    gpu = [a for a in atomics if a.endswith(".GPU")]
-    cta = [a for a in atomics if a.endswith(".SM") or a.endswith(".CTA")]
-    assert len(gpu) >= 6, atomics      # u32 add x3, f64 add, max, cas
-    assert len(cta) == 1, atomics      # the single hierarchy::Threads add
+    per_kernel, cur = {}, None
+    for line in text.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = []
+        elif cur:
+            per_kernel[cur] += re.findall(r"\b(?:ATOMG|REDG|ATOM|RED)\.[\w.]+", line)
+    blocks = {k: v for k, v in per_kernel.items() if "CountBlocksKernel" in k}
+    threads = {k: v for k, v in per_kernel.items() if "CountThreadsKernel" in k}
+    assert blocks and threads  # plain and coarsened trampolines of both functors
+    for k, atomics in blocks.items():
+        assert len(atomics) >= 6 and all(a.endswith(".GPU") for a in atomics), (k, atomics)  # u32 add x3, f64 add, max, cas
+    for k, atomics in threads.items():
+        assert atomics and all(a.endswith(".SM") or a.endswith(".CTA") for a in atomics), (k, atomics)
