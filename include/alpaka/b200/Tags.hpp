@@ -14,6 +14,7 @@
 
 #include "Vec.hpp"
 
+#include <concepts>
 #include <iostream>
 #include <string>
 #include <tuple>
@@ -124,8 +125,12 @@ namespace alpaka
 
     namespace concepts
     {
+        //! a tag: an InterfaceTag that can be default-constructed and names itself (reference: acc/Tag.hpp:43-53 --
+        //! deriving from InterfaceTag alone is not enough, nor is a get_name() on an unrelated type)
         template<typename T>
-        concept Tag = std::is_base_of_v<InterfaceTag, T>;
+        concept Tag = std::derived_from<T, InterfaceTag> && std::default_initializable<T> && requires {
+            { T::get_name() } -> std::same_as<std::string>;
+        };
     } // namespace concepts
 
     template<typename T>
@@ -164,6 +169,12 @@ namespace alpaka
 
     //! the tags that have an accelerator in this build: exactly one
     using EnabledAccTags = std::tuple<TagGpuB200>;
+
+    //! true iff an accelerator stands behind the tag, i.e. trait::TagToAcc maps it (reference: acc/TagAccIsEnabled.hpp:24-35)
+    template<concepts::Tag TTag>
+    struct AccIsEnabled : std::bool_constant<requires { typename trait::TagToAcc<TTag, DimInt<1u>, int>::type; }>
+    {
+    };
 
     namespace detail
     {

@@ -13,6 +13,32 @@
 
 namespace alpaka::test
 {
+    namespace detail
+    {
+        //! The reference's per-back-end aliases "the accelerator if its back-end is enabled, else int"
+        //! (test/acc/TestAccs.hpp:29-101), which its tag tests enumerate: one back-end is enabled here.
+        template<typename TDim, typename TIdx>
+        using AccGpuCudaRtIfAvailableElseInt = AccGpuCudaRt<TDim, TIdx>;
+        template<typename TDim, typename TIdx>
+        using AccCpuSerialIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccCpuThreadsIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccCpuTbbIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccCpuOmp2BlocksIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccCpuOmp2ThreadsIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccGpuHipRtIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccCpuSyclIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccFpgaSyclIntelIfAvailableElseInt = int;
+        template<typename TDim, typename TIdx>
+        using AccGpuSyclIntelIfAvailableElseInt = int;
+    } // namespace detail
+
     //! A std::tuple containing all enabled accelerators for the given dimensionality and index type.
     template<typename TDim, typename TIdx>
     using EnabledAccs = std::tuple<AccGpuB200<TDim, TIdx>>;
