@@ -22,6 +22,7 @@ namespace b200
     int64_t tune(char const* key, int64_t dflt);
     int smCount(int dev);
     int currentDevice();
+    int useDeviceOf(cudaStream_t s); // makes the stream's device current (multi-device processes)
 
     inline void countLaunch()
     {

@@ -319,6 +319,8 @@ namespace
         B200_REQUIRE(n == 0 || (a && (!DOT || b)), B200_EINVAL);
         B200_REQUIRE(reinterpret_cast<uintptr_t>(scratch) % 16 == 0, B200_EALIGN);
         auto const s = reinterpret_cast<cudaStream_t>(stream);
+        if(int const rc = b200::useDeviceOf(s))
+            return rc;
         constexpr int N = 32 / int(sizeof(T));
         bool const aligned
             = reinterpret_cast<uintptr_t>(a) % 32 == 0 && (!DOT || reinterpret_cast<uintptr_t>(b) % 32 == 0);

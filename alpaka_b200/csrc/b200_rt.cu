@@ -79,6 +79,23 @@ namespace b200
         return it == tuneMap().end() ? dflt : it->second;
     }
 
+    // The kernel entries of the ABI take a stream, not a device (b200_stream_*, b200_dot_*, b200_reduce_*): make the
+    // stream's device current before the launch, so that one process can drive several devices (the reference sets the
+    // device in front of every call, e.g. kernel/TaskKernelGpuUniformCudaHipRt.hpp:265). The NULL stream keeps the
+    // current device.
+    int useDeviceOf(cudaStream_t s)
+    {
+        if(s == nullptr)
+            return 0;
+        int dev = -1;
+        cudaError_t e = cudaStreamGetDevice(s, &dev);
+        if(e == cudaSuccess && dev != currentDevice())
+            e = cudaSetDevice(dev);
+        if(e != cudaSuccess)
+            return cudaFail(e, "cudaStreamGetDevice / cudaSetDevice", __FILE__, __LINE__);
+        return 0;
+    }
+
     int currentDevice()
     {
         int d = 0;

@@ -423,6 +423,8 @@ namespace
         if(n == 0)
             return 0;
         auto const s = reinterpret_cast<cudaStream_t>(stream);
+        if(int const rc = b200::useDeviceOf(s))
+            return rc;
         StreamCfg cfg = streamCfg(name, int(sizeof(T)));
         if(cfg.block < 32 || cfg.block % 32 != 0 || cfg.block > (cfg.unroll == 1 ? 1024 : 512))
             return b200::fail(B200_EINVAL, "stream.block must be a multiple of 32 in [32,1024] (<= 512 when stream.unroll > 1)", __FILE__, __LINE__);

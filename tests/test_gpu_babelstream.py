@@ -152,10 +152,11 @@ def test_dot_within_tolerance_of_reference_order(gpu, dtype, n):
     assert abs(float(ph.astype(np.float64).sum()) - float(want_cpu)) <= rtol * scale
 
 
-def test_dot_positive_data_relative_to_value(gpu):
-    """With positive data the 1e-12 bound holds relative to the result itself."""
+@pytest.mark.parametrize("n", [1 << 24, 1 << 25], ids=["2^24", "2^25_C1"])
+def test_dot_positive_data_relative_to_value(gpu, n):
+    """BASELINE.json north_star, read literally: Dot within 1e-12 RELATIVE TO THE RESULT (positive data, so the sum does not
+    cancel), against the reference's order on its CPU back-end ({256,1,1}) -- at C1's 2^25 too (2^30: test_gpu_full_size)."""
     ab, dev, queue = gpu
-    n = 1 << 24
     a = np.abs(ol.fill("uniform_f64", n, seed=31)) + 0.5
     b = np.abs(ol.fill("uniform_f64", n, seed=32)) + 0.5
     want = ol.oracle().orc_dot_f64(P(a), P(b), n, 256, 1, None)

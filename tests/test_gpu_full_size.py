@@ -17,6 +17,34 @@ import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 
 
+def test_c2_dot_2pow30_within_1e12_of_the_result(gpu):
+    """BASELINE.json north_star, read literally, at C2's size: Dot of 2^30 POSITIVE hashed doubles within 1e-12 relative to the
+    result itself, against the reference's summation orders (CPU back-end {256,1,1} and GPU shape {256,1024})."""
+    ab, dev, queue = gpu
+    from oracle_lib import P
+
+    n = 1 << 30
+    a = ol.fill("uniform_f64", n, seed=41)
+    np.abs(a, out=a)
+    a += 0.5
+    b = ol.fill("uniform_f64", n, seed=42)
+    np.abs(b, out=b)
+    b += 0.5
+    want_cpu = float(ol.oracle().orc_dot_f64(P(a), P(b), n, 256, 1, None))
+    want_gpu_shape = float(ol.oracle().orc_dot_f64(P(a), P(b), n, 256, 1024, None))
+    da, db = (ab.alloc_buf(dev, np.float64, n, queue) for _ in range(2))
+    try:
+        ab.memcpy(queue, da, a)
+        ab.memcpy(queue, db, b)
+        got = float(ab.babelstream.dot(queue, da, db))
+        assert abs(got - want_cpu) <= 1e-12 * abs(want_cpu), (got, want_cpu)
+        assert abs(got - want_gpu_shape) <= 1e-12 * abs(want_gpu_shape), (got, want_gpu_shape)
+    finally:
+        da.free()
+        db.free()
+        queue.wait()
+
+
 def test_c2_babelstream_2pow30_known_answers_and_window_parity(gpu):
     ab, dev, queue = gpu
     bs = ab.babelstream
