@@ -92,7 +92,9 @@ namespace b200
     }
 
     // ---- 128-bit and 256-bit global accesses with streaming cache policy.
-    // HINT: 0 = default, 1 = ld.nc / L1::no_allocate + st .cs (evict-first streaming)
+    // HINT: 0 = default, 1 = ld.nc / L1::no_allocate + st .cs (evict-first streaming),
+    //       2 (256-bit loads only) = ld.nc / L1::no_allocate / L2::evict_last: the lines just read stay behind the dirty
+    //         lines of the stores in the L2's replacement order -- Triad/Add 7153 vs 7131 GB/s (profiles/r02/tune_stream_fine.log)
     template<int HINT>
     __device__ __forceinline__ void ldg128(void const* p, uint32_t (&r)[4])
     {
@@ -127,6 +129,10 @@ namespace b200
     {
         if constexpr(HINT == 0)
             asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                         : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3])
+                         : "l"(p));
+        else if constexpr(HINT == 2)
+            asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v4.u64 {%0,%1,%2,%3}, [%4];"
                          : "=l"(r[0]), "=l"(r[1]), "=l"(r[2]), "=l"(r[3])
                          : "l"(p));
         else

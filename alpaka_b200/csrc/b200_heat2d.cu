@@ -676,7 +676,7 @@ namespace
     //     step); that is what made four levels per launch faster than three.
     //   * ring cells of intermediate level k take tf[k] * (sx + sy); only tiles touching the field edge test per cell.
     // Stand-alone fields (padY = 1) and row slabs whose ghost rows are at least S deep (padY >= S, fused halo exchange).
-    constexpr int kMaxLevels = 4;
+    constexpr int kMaxLevels = 8; // the tile kernel below: 3 or 4; the walker further down: 4, 6 or 8
 
     template<int S>
     struct StepNGeom
@@ -958,6 +958,395 @@ namespace
         }
     }
 
+    // ------------------------------------------------------------------------------------------------------------
+    // S time levels per launch by WALKERS, S even (4, 6, 8): the round-2 replacement of the tile kernel above for even S.
+    // ncu on heatStepNKernel<4,16,2> (profiles/r02): FP64 pipe 70 %, DRAM 66 %, 1.45 x the minimal DP instructions -- a
+    // 16-row tile recomputes (16 + 2S)/16 of the rows of the lower levels and reloads as many input rows; and with two
+    // columns per lane the four SHFL.32 per level, the register moves around them and the addressing take as many issue slots
+    // as the DP instructions themselves (an SMSP issues one instruction per cycle, the FP64 pipe takes one per two).
+    // Here ONE WARP walks down a 128-column window (FOUR columns per lane) over a tall row segment and never looks at a row
+    // twice: the row redundancy is 2S per SEGMENT, the column redundancy 128/(128 - 8 ceil(S/4)), and the shuffles are
+    // shared by twice as many cells.
+    //   * no CTA-wide synchronisation at all: every warp owns a ring of ST shared-memory stages of R rows x 128 columns
+    //     (1 KB per row), filled by its own TMA copies (one elected lane, one mbarrier per stage, refilled as soon as
+    //     the warp has consumed the stage); a CTA is just four independent walkers side by side;
+    //   * per input row two LDS.128 per lane, then one "arrival" per level: the state a level keeps between rows is 2 doubles
+    //     per cell -- the partial sum q = ((c*k + l*rX) + r*rX) + u*rY of the row waiting for the row below it, and that
+    //     row's product with rY for its successor -- instead of the 4 of the tile kernel (RowN + U), because everything a
+    //     stencil takes from its own row and the row above is folded in when the row is CREATED; the row below then
+    //     completes it with one addition. Same IEEE products, same order of additions (StencilKernel.hpp:84-86 left to
+    //     right), same bits. The dependent chain from level to level is add -> mul (was mul -> 4 add);
+    //   * 6 DP instructions per cell and level on square cells (8 mul + 16 add per lane quad), two 64-bit shuffles per
+    //     level and lane (the outer products of the quad);
+    //   * rows of a level the walk has not produced yet (the first 2S input rows of a segment) flow through as finite
+    //     garbage that no stored cell depends on: no prologue code, the segment's row range guards the stores. Chunks whose
+    //     rows are all core rows run bare (interior windows) or with the ring columns patched per lane (edge windows; the
+    //     row factors sy[j] roll through registers one row ahead, so no load sits in the dependent chain); rows next to the
+    //     ring, ghost zones and slab strips take the CAREFUL path (ring values, store guards, peer stores);
+    //   * slabs: the strip rows (my first / last G core rows = the neighbours' ghost rows) are short segments of their own at
+    //     the front of the grid, so the flags go out while the interior walkers are still under way.
+    struct HeatWArgs : HeatNArgs
+    {
+        uint32_t nWin; // column windows
+        uint32_t nEdgeRight; // windows at the right end that hold ring columns or columns beyond the field (window 0 is the left one)
+        uint32_t nSegAll; // segments per window, strips included
+        uint32_t nStrip; // strip segments at the front of the segment order
+        int32_t stripY0[2], stripY1[2]; // their output rows [y0, y1)
+        int32_t intY0, intY1, segRows; // interior output rows [intY0, intY1) in segments of segRows
+        uint32_t nWalkers;
+        int32_t rows; // rows of the array (sy has that many entries)
+        int32_t align32; // 1: rows of dst (and of the peers' arrays) are 32-byte aligned -> 256-bit stores
+        double sxLeft, sxRight; // sx[0], sx[nx+1]: the ring columns' factors
+    };
+
+    constexpr int kWalkCols = 4; // columns per lane
+
+    template<int S>
+    struct WalkGeom
+    {
+        static constexpr int LOST = (S + 3) / 4; // lanes per side whose columns the levels invalidate
+        static constexpr int WW = 32 * kWalkCols - 2 * kWalkCols * LOST; // output columns per window
+    };
+
+    template<int S>
+    struct WalkState
+    {
+        double q[S][kWalkCols]; // the waiting row of level l: ((c*k + left*rX) + right*rX) + up*rY, lacking only down*rY
+        double u[S][kWalkCols]; // its products with rY: the up terms of the row that arrives next
+    };
+
+    // A new row v[] of some level arrives: it completes the waiting row (-> one row of the next level, returned in v) and
+    // becomes the waiting row itself.
+    template<bool SQ>
+    __device__ __forceinline__ void walkArrive(double (&v)[kWalkCols], double k, double rX, double rY, double (&q)[kWalkCols], double (&u)[kWalkCols])
+    {
+        double h[kWalkCols], w[kWalkCols], o[kWalkCols];
+#pragma unroll
+        for(int i = 0; i < kWalkCols; ++i)
+        {
+            h[i] = __dmul_rn(v[i], rX);
+            w[i] = SQ ? h[i] : __dmul_rn(v[i], rY);
+        }
+        double const lh = shflUp1(h[kWalkCols - 1]), rh = shflDown1(h[0]);
+#pragma unroll
+        for(int i = 0; i < kWalkCols; ++i)
+        {
+            o[i] = __dadd_rn(q[i], w[i]);
+            double const left = i == 0 ? lh : h[i - 1], right = i == kWalkCols - 1 ? rh : h[i + 1];
+            double const p = __dadd_rn(__dadd_rn(__dmul_rn(v[i], k), left), right);
+            q[i] = __dadd_rn(p, u[i]);
+            u[i] = w[i];
+        }
+#pragma unroll
+        for(int i = 0; i < kWalkCols; ++i)
+            v[i] = o[i];
+    }
+
+    enum WalkMode
+    {
+        kWalkBare, // interior window, all rows core rows: no tests but the segment's row range
+        kWalkEdgeCols, // edge window, all rows core rows: ring columns per lane
+        kWalkCareful // anything: ring rows, ghost zones, slab strips with peer stores
+    };
+
+    template<int HINT>
+    __device__ __forceinline__ void storeQuad(double* p, double const (&v)[kWalkCols], bool align32)
+    {
+        if(align32)
+        {
+            if constexpr(HINT)
+                asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+            else
+                asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+        }
+        else
+        {
+            stg2<HINT>(p, v[0], v[1]);
+            stg2<HINT>(p + 2, v[2], v[3]);
+        }
+    }
+
+    // One input row j0 (level 0) through all S levels; stores row j0 - S of level S into `out` (= its address for this
+    // lane's quad). [ya, yb) are the output rows of the walker's segment. ringMask / validMask: bit i = column gi + i is a
+    // ring column / lies in [0, nx+1] (edge windows). syw[l] = sy[j0 - 1 - l] (edge windows, all rows core).
+    template<int S, bool SQ, WalkMode MODE>
+    __device__ __forceinline__ void walkRow(HeatWArgs const& A, WalkState<S>& st, double (&v)[kWalkCols], int32_t j0, int32_t gi, bool storeLane, int32_t ya, int32_t yb, double* out, uint32_t ringMask, uint32_t validMask, double const (&syw)[S])
+    {
+#pragma unroll
+        for(int l = 0; l < S; ++l)
+        {
+            walkArrive<SQ>(v, A.k, A.rX, A.rY, st.q[l], st.u[l]);
+            int32_t const gj = j0 - (l + 1); // row of the new level-(l+1) values, now in v
+            if constexpr(MODE == kWalkEdgeCols)
+            {
+                // rows are core rows: the only cells the stencil does not produce are the ring columns
+                if(ringMask != 0u)
+                {
+#pragma unroll
+                    for(int i = 0; i < kWalkCols; ++i)
+                        if(ringMask & (1u << i))
+                            v[i] = __dmul_rn(A.tf[l], __dadd_rn(gi + i == 0 ? A.sxLeft : A.sxRight, syw[l]));
+                }
+            }
+            if(l + 1 < S)
+            {
+                if constexpr(MODE == kWalkCareful)
+                {
+                    // rows on which level l+1 is defined: the core rows, and on a side with a neighbour the S-(l+1) rows
+                    // beyond them that deeper levels still need
+                    int32_t const jLo = A.loY - (S - (l + 1)) * A.ghostTop, jHi = A.hiY + (S - (l + 1)) * A.ghostBottom;
+                    bool const jDefined = gj >= jLo && gj <= jHi;
+#pragma unroll
+                    for(int i = 0; i < kWalkCols; ++i)
+                        if(!(jDefined && gi + i >= 1 && gi + i <= int32_t(A.nx)))
+                            v[i] = ringOrZeroN(A, gj, gi + i, jLo, jHi, A.tf[l]);
+                }
+            }
+            else if(storeLane && gj >= ya && gj < yb)
+            {
+                if constexpr(MODE == kWalkBare)
+                    storeQuad<1>(out, v, A.align32 != 0);
+                else if constexpr(MODE == kWalkEdgeCols)
+                {
+                    if(validMask == 0xfu)
+                        storeQuad<1>(out, v, A.align32 != 0);
+                    else
+                    {
+#pragma unroll
+                        for(int i = 0; i < kWalkCols; ++i)
+                            if(validMask & (1u << i))
+                                out[i] = v[i];
+                    }
+                }
+                else
+                {
+                    bool const jCore = gj >= A.loY && gj <= A.hiY;
+                    bool const jRing = (gj == A.loY - 1 && !A.ghostTop) || (gj == A.hiY + 1 && !A.ghostBottom);
+                    uint32_t wr = 0u; // cells to write: core or ring; corners and cells beyond the field have neither
+#pragma unroll
+                    for(int i = 0; i < kWalkCols; ++i)
+                    {
+                        int32_t const c = gi + i;
+                        if((jCore || jRing) && c >= 0 && c <= int32_t(A.nx) + 1)
+                        {
+                            bool const iCore = c >= 1 && c <= int32_t(A.nx);
+                            if(!(jCore && iCore))
+                                v[i] = ringOrZeroN(A, gj, c, A.loY, A.hiY, A.tf[S - 1]);
+                            if(jCore || iCore)
+                                wr |= 1u << i;
+                        }
+                    }
+                    // fused halo exchange, as in the tile kernel: my first / last `sendRows` core rows (ring columns
+                    // included) are the neighbours' ghost rows
+                    double* peer = nullptr;
+                    if(jCore && wr != 0u)
+                    {
+                        if(A.peerDst[0] != nullptr && gj < A.loY + A.sendRows)
+                            peer = A.peerDst[0] + int64_t(gj + int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
+                        else if(A.peerDst[1] != nullptr && gj > A.hiY - A.sendRows)
+                            peer = A.peerDst[1] + int64_t(gj - int32_t(A.ny)) * int64_t(A.pitchElems) + gi;
+                    }
+                    if(wr == 0xfu)
+                    {
+                        storeQuad<1>(out, v, A.align32 != 0);
+                        if(peer != nullptr)
+                            storeQuad<0>(peer, v, A.align32 != 0);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for(int i = 0; i < kWalkCols; ++i)
+                            if(wr & (1u << i))
+                            {
+                                out[i] = v[i];
+                                if(peer != nullptr)
+                                    peer[i] = v[i];
+                            }
+                    }
+                }
+            }
+        }
+    }
+
+    constexpr int kWalkWarps = 4; // walkers per CTA
+
+    // MINB: CTAs per SM the register allocation is held to (128 threads: 4 -> 128 registers, 3 -> 168, 2 -> 255)
+    template<int S, int R, int ST, bool SQ, int MINB>
+    __global__ void __launch_bounds__(32 * kWalkWarps, MINB) heatWalkKernel(const __grid_constant__ CUtensorMap mapSrc, HeatWArgs const A)
+    {
+        static_assert(S % 2 == 0 && S >= 2 && S <= kMaxLevels, "even S");
+        using G = WalkGeom<S>;
+        constexpr int BOXX = 32 * kWalkCols;
+        constexpr uint32_t kStageBytes = uint32_t(BOXX) * R * 8u;
+        extern __shared__ __align__(128) unsigned char smem[];
+        __shared__ uint64_t full[kWalkWarps][ST];
+        int const warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+        uint32_t const walker = blockIdx.x * kWalkWarps + warp;
+        if(walker >= A.nWalkers)
+            return; // (no CTA-wide barrier anywhere in this kernel)
+        // walker order: the edge windows of every segment first (they run the slower ring-column path; dispatched last they
+        // would be the tail of the launch), then the interior windows segment by segment (strip segments first)
+        uint32_t const nEdge = 1u + A.nEdgeRight, nEdgeWalkers = nEdge * A.nSegAll;
+        uint32_t seg, w;
+        if(walker < nEdgeWalkers)
+        {
+            seg = walker / nEdge;
+            uint32_t const e = walker - seg * nEdge;
+            w = e == 0u ? 0u : A.nWin - e;
+        }
+        else
+        {
+            uint32_t const idx = walker - nEdgeWalkers, nInner = A.nWin - nEdge;
+            seg = idx / nInner;
+            w = 1u + (idx - seg * nInner);
+        }
+        bool const strip = seg < A.nStrip;
+        int32_t ya, yb;
+        if(strip)
+        {
+            ya = A.stripY0[seg];
+            yb = A.stripY1[seg];
+        }
+        else
+        {
+            ya = A.intY0 + int32_t(seg - A.nStrip) * A.segRows;
+            yb = min(ya + A.segRows, A.intY1);
+        }
+        unsigned char* const stages = smem + size_t(warp) * ST * kStageBytes;
+        uint64_t* const bar = full[warp];
+        int32_t const cx = int32_t(w) * G::WW - kWalkCols * G::LOST; // global column of lane 0's quad
+        int32_t const gi = cx + kWalkCols * lane;
+        int32_t const rowStart = ya - S; // first input row
+        int32_t const nChunks = (yb - ya + 2 * S + R - 1) / R;
+        if(lane == 0)
+        {
+#pragma unroll
+            for(int s = 0; s < ST; ++s)
+                mbarInit(&bar[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            // strip walkers read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
+            if(strip && A.myFlags != nullptr)
+                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
+#pragma unroll
+            for(int s = 0; s < ST; ++s)
+                if(s < nChunks)
+                {
+                    mbarExpectTx(&bar[s], kStageBytes);
+                    tmaLoad2d(stages + s * kStageBytes, &mapSrc, cx, rowStart + s * R, &bar[s]);
+                }
+        }
+        __syncwarp();
+
+        bool const storeLane = lane >= G::LOST && lane < 32 - G::LOST;
+        // every column of the window is a core column
+        bool const colInterior = cx >= 1 && cx + BOXX - 1 <= int32_t(A.nx);
+        uint32_t ringMask = 0u, validMask = 0u;
+#pragma unroll
+        for(int i = 0; i < kWalkCols; ++i)
+        {
+            int32_t const c = gi + i;
+            if(c == 0 || c == int32_t(A.nx) + 1)
+                ringMask |= 1u << i;
+            if(c >= 0 && c <= int32_t(A.nx) + 1)
+                validMask |= 1u << i;
+        }
+        WalkState<S> st;
+#pragma unroll
+        for(int l = 0; l < S; ++l)
+#pragma unroll
+            for(int i = 0; i < kWalkCols; ++i)
+                st.q[l][i] = st.u[l][i] = 0.0;
+        // sy[j] one row ahead of its use (edge windows): syw[l] = sy[j0 - 1 - l] at input row j0
+        auto const syAt = [&](int32_t j) { return __ldg(A.sy + min(max(j, 0), A.rows - 1)); };
+        double syw[S];
+        if(!colInterior)
+        {
+#pragma unroll
+            for(int l = 0; l < S; ++l)
+                syw[l] = syAt(rowStart - 1 - l);
+        }
+        else
+        {
+#pragma unroll
+            for(int l = 0; l < S; ++l)
+                syw[l] = 0.0;
+        }
+
+        int stage = 0;
+        uint32_t parity = 0;
+        int64_t const pitch = int64_t(A.pitchElems);
+        double* outRow = A.dst + int64_t(rowStart - S) * pitch + gi; // output address of the row that input row rowStart completes
+        for(int32_t c = 0; c < nChunks; ++c)
+        {
+            int32_t const r0 = rowStart + c * R; // first input row of the chunk
+            mbarWait(&bar[stage], parity);
+            double const* rowp = reinterpret_cast<double const*>(stages + stage * kStageBytes) + kWalkCols * lane;
+            // every row this chunk produces at any level (r0 - S .. r0 + R - 2) is a core row: nothing but the stencil there,
+            // except in the ring columns of an edge window. (Rows of the segment's prologue hold finite garbage that no
+            // stored cell depends on; the row range [ya, yb) guards the stores.)
+            bool const rowsCore = !strip && r0 - S >= A.loY && r0 + R - 2 <= A.hiY;
+            if(rowsCore && colInterior)
+            {
+#pragma unroll
+                for(int r = 0; r < R; ++r)
+                {
+                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
+                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    walkRow<S, SQ, kWalkBare>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
+                }
+            }
+            else if(rowsCore)
+            {
+#pragma unroll
+                for(int r = 0; r < R; ++r)
+                {
+                    double const syNext = syAt(r0 + r); // sy[j0]: the newest entry of the NEXT row's window
+                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
+                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    walkRow<S, SQ, kWalkEdgeCols>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
+#pragma unroll
+                    for(int l = S - 1; l > 0; --l)
+                        syw[l] = syw[l - 1];
+                    syw[0] = syNext;
+                }
+            }
+            else
+            {
+#pragma unroll 1
+                for(int r = 0; r < R; ++r)
+                {
+                    double const syNext = syAt(r0 + r);
+                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
+                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    walkRow<S, SQ, kWalkCareful>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
+#pragma unroll
+                    for(int l = S - 1; l > 0; --l)
+                        syw[l] = syw[l - 1];
+                    syw[0] = syNext;
+                }
+            }
+            outRow += R * pitch;
+            __syncwarp();
+            if(lane == 0 && c + ST < nChunks)
+            {
+                mbarExpectTx(&bar[stage], kStageBytes);
+                tmaLoad2d(stages + stage * kStageBytes, &mapSrc, cx, r0 + ST * R, &bar[stage]);
+            }
+            if(++stage == ST)
+            {
+                stage = 0;
+                parity ^= 1u;
+            }
+        }
+
+        if(strip && A.stripCounter != nullptr)
+        {
+            __syncwarp();
+            if(lane == 0)
+                publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
+        }
+    }
+
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
     // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
     __global__ void __launch_bounds__(256) heatBoundaryKernel(HeatArgs const A)
@@ -1073,12 +1462,184 @@ struct b200_heat2d_plan_st
     int map2Tyt = 0;
     CUtensorMap mapN[2]; // N-level kernel: box keyed by mapNKey = levels * 1000 + tile rows (0 = not built yet)
     int mapNKey = 0;
+    CUtensorMap mapW[2]; // walker kernel: box 128 columns x R rows, keyed by mapWKey = R (0 = not built yet)
+    int mapWKey = 0;
+    double sxLeft = 0.0, sxRight = 0.0; // sx[0], sx[nx+1] (host copies for the walker's edge windows)
     uint32_t padY = 1; // 1: reference layout (ny+2 rows); 2: row slab with ghost rows two deep (ny+4 rows)
     // fused halo exchange (b200_heat2d_plan_set_halo)
     bool hasHalo = false;
     b200_heat2d_halo halo{};
     uint32_t* haloScratch = nullptr; // [0] strip-tile counter, [1] status
 };
+
+namespace
+{
+    // ---- the walker form of an S-level launch (heatWalkKernel), S = 4, 6, 8
+    template<int S, int R, int ST, int MINB>
+    int launchWalkShape(b200_heat2d_plan_t plan, cudaStream_t s, int src_index, HeatWArgs& A, bool sq)
+    {
+        constexpr int WW = WalkGeom<S>::WW;
+        constexpr int BOXX = 32 * kWalkCols;
+        constexpr size_t smemBytes = size_t(kWalkWarps) * ST * R * BOXX * 8;
+        auto* const kSq = heatWalkKernel<S, R, ST, true, MINB>;
+        auto* const kGen = heatWalkKernel<S, R, ST, false, MINB>;
+        auto* const kernel = sq ? kSq : kGen;
+        static std::mutex mtx;
+        static int slotsPerSm[2][64] = {}; // [sq][device]: resident walkers per SM (0 = not asked yet)
+        int slots;
+        {
+            std::lock_guard<std::mutex> lock(mtx);
+            int& cached = slotsPerSm[sq ? 1 : 0][plan->dev & 63];
+            if(cached == 0)
+            {
+                B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes)));
+                int ctas = 0;
+                B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, kernel, 32 * kWalkWarps, smemBytes));
+                cached = (ctas > 0 ? ctas : 1) * kWalkWarps;
+            }
+            slots = cached * b200::smCount(plan->dev);
+        }
+        uint32_t const rows = plan->ny + 2 * plan->padY;
+        if(plan->mapWKey != R)
+        {
+            EncodeTiledFn const enc = encoder();
+            if(!enc)
+                return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
+            for(int b = 0; b < 2; ++b)
+                if(!encodeFieldMap(enc, &plan->mapW[b], plan->u[b], plan->pitchBytes, rows, plan->nx, R, BOXX))
+                    return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (walker box)", __FILE__, __LINE__);
+            plan->mapWKey = R;
+        }
+        A.rows = int32_t(rows);
+        A.sxLeft = plan->sxLeft;
+        A.sxRight = plan->sxRight;
+        auto aligned32 = [](void const* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 32 == 0; };
+        A.align32 = plan->pitchBytes % 32 == 0 && aligned32(A.dst) && aligned32(A.peerDst[0]) && aligned32(A.peerDst[1]) ? 1 : 0;
+        A.nWin = (plan->nx + 2 + uint32_t(WW) - 1) / uint32_t(WW);
+        // edge windows: window 0 (its first lanes lie left of the field) and the windows at the right end whose 128 columns
+        // reach beyond column nx; at least one window is counted on the left, the rest of the edge windows on the right
+        A.nEdgeRight = 0;
+        while(A.nEdgeRight + 1 < A.nWin
+              && int64_t(A.nWin - 1 - A.nEdgeRight) * WW - kWalkCols * WalkGeom<S>::LOST + BOXX - 1 > int64_t(plan->nx))
+            ++A.nEdgeRight;
+        // output rows: the core rows, plus the ring row on a physical side; strips = the rows sent to a neighbour
+        int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
+        A.nStrip = 0;
+        if(A.ghostTop)
+        {
+            A.stripY0[A.nStrip] = A.loY;
+            A.stripY1[A.nStrip] = A.loY + A.sendRows;
+            outLo = A.loY + A.sendRows;
+            ++A.nStrip;
+        }
+        if(A.ghostBottom)
+        {
+            A.stripY0[A.nStrip] = A.hiY + 1 - A.sendRows;
+            A.stripY1[A.nStrip] = A.hiY + 1;
+            outHi = A.hiY - A.sendRows;
+            ++A.nStrip;
+        }
+        A.intY0 = outLo;
+        A.intY1 = outHi + 1;
+        int64_t const rowsInt = int64_t(A.intY1) - A.intY0;
+        uint32_t nSeg = 0;
+        A.segRows = 1;
+        if(rowsInt > 0)
+        {
+            // Segments per window: maximise (share of the resident-walker slots used over all waves) x (share of a walker's
+            // rows that are not its 2S-row prologue) x waves / (waves + 0.3) -- the last factor models the tail a slower
+            // (edge-window) walker of the last wave leaves; it favours a few waves over exactly one. heat.walk_seg_rows
+            // overrides.
+            int64_t const forced = b200::tune("heat.walk_seg_rows", 0);
+            int64_t best = rowsInt;
+            double bestScore = -1.0;
+            int64_t const maxSeg = forced > 0 ? 0 : (rowsInt + 15) / 16;
+            for(int64_t k = 1; k <= maxSeg && k <= 8192; ++k)
+            {
+                int64_t const segRows = (rowsInt + k - 1) / k;
+                int64_t const segs = (rowsInt + segRows - 1) / segRows;
+                double const walkers = double(segs) * A.nWin;
+                double const waves = double((int64_t(walkers) + slots - 1) / slots);
+                double const score = walkers / (waves * slots) * double(segRows) / double(segRows + 2 * S) * waves / (waves + 0.3);
+                if(score > bestScore + 1e-9)
+                {
+                    bestScore = score;
+                    best = segRows;
+                }
+            }
+            A.segRows = int32_t(forced > 0 ? forced : best);
+            nSeg = uint32_t((rowsInt + A.segRows - 1) / A.segRows);
+        }
+        A.nSegAll = A.nStrip + nSeg;
+        uint64_t const walkers = uint64_t(A.nSegAll) * A.nWin;
+        B200_REQUIRE(walkers <= 0x7fffffffull, B200_ERANGE);
+        A.nWalkers = uint32_t(walkers);
+        A.stripTiles = A.nStrip * A.nWin; // strip WALKERS: each counts itself once
+        unsigned const grid = unsigned((walkers + kWalkWarps - 1) / kWalkWarps);
+        kernel<<<grid, 32 * kWalkWarps, smemBytes, s>>>(plan->mapW[src_index], A);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int launchWalk(b200_heat2d_plan_t plan, cudaStream_t s, int src_index, HeatNArgs const& base, int levels, bool sq)
+    {
+        HeatWArgs A{};
+        static_cast<HeatNArgs&>(A) = base;
+        // R * 10 + ST; 0 = the default: 4 rows x 4 stages = 64 KB per CTA (measured best at every depth, 16384^2 over 960 steps:
+        // 8 levels 174.5 / 175.1 / 182.5 us per step with 3 / 4 / 6 stages; profiles/r02/heat_walk_probe.log)
+        int shape = int(b200::tune("heat.walk_shape", 0));
+        if(shape == 0)
+            shape = 44;
+        // CTAs per SM the registers are budgeted for: 0 = the default of the depth (4 levels: 3, 6: 2, 8: 2)
+        int minb = int(b200::tune("heat.walk_minb", 0));
+        if(minb == 0)
+            minb = levels == 4 ? 3 : 2;
+        auto go = [&]<int S_, int R_, int ST_>() -> int
+        {
+            if constexpr(S_ == 4)
+            {
+                if(minb >= 4)
+                    return launchWalkShape<S_, R_, ST_, 4>(plan, s, src_index, A, sq);
+                return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
+            }
+            else
+            {
+                if(minb >= 3)
+                    return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
+                return launchWalkShape<S_, R_, ST_, 2>(plan, s, src_index, A, sq);
+            }
+        };
+        switch(levels * 100 + shape)
+        {
+        case 443:
+            return go.template operator()<4, 4, 3>();
+        case 444:
+            return go.template operator()<4, 4, 4>();
+        case 426:
+            return go.template operator()<4, 2, 6>();
+        case 446:
+            return go.template operator()<4, 4, 6>();
+        case 643:
+            return go.template operator()<6, 4, 3>();
+        case 644:
+            return go.template operator()<6, 4, 4>();
+        case 626:
+            return go.template operator()<6, 2, 6>();
+        case 646:
+            return go.template operator()<6, 4, 6>();
+        case 843:
+            return go.template operator()<8, 4, 3>();
+        case 844:
+            return go.template operator()<8, 4, 4>();
+        case 826:
+            return go.template operator()<8, 2, 6>();
+        case 846:
+            return go.template operator()<8, 4, 6>();
+        default:
+            return b200::fail(B200_EINVAL, "heat.walk_shape: supported 43, 44, 46, 26 (rows per stage x 10 + stages)", __FILE__, __LINE__);
+        }
+    }
+} // namespace
 
 extern "C"
 {
@@ -1117,6 +1678,8 @@ extern "C"
             plan->nx = nx;
             plan->edges = edges;
             plan->padY = padY;
+            plan->sxLeft = sx_host[0];
+            plan->sxRight = sx_host[size_t(nx) + 1];
             uint64_t const rows = uint64_t(ny) + 2 * padY;
             for(int b = 0; b < 2; ++b)
             {
@@ -1472,6 +2035,8 @@ extern "C"
         int launchStepN(b200_heat2d_plan_t plan, b200_stream_t stream, int src_index, double rx, double ry, int levels, double const* tfs, uint32_t haloStep)
         {
             B200_CUDA(cudaSetDevice(plan->dev));
+            // even depths from 4 on: the walker kernel (heat.walk = 0 keeps the round-1 tile kernel for 4 levels)
+            bool const walk = levels >= 4 && levels % 2 == 0 && (levels > 4 || b200::tune("heat.walk", 1) != 0);
             int const rpt = int(b200::tune("heat.stepn_rpt", 16));
             int const nwy = int(b200::tune("heat.stepn_nwy", 2));
             int const tyt = rpt * nwy;
@@ -1479,7 +2044,7 @@ extern "C"
             int const wout = levels == 3 ? StepNGeom<3>::WOUT : StepNGeom<4>::WOUT;
             uint32_t const rows = plan->ny + 2 * plan->padY;
             int const key = levels * 1000 + tyt;
-            if(plan->mapNKey != key)
+            if(!walk && plan->mapNKey != key)
             {
                 EncodeTiledFn const enc = encoder();
                 if(!enc)
@@ -1538,6 +2103,8 @@ extern "C"
             uint64_t const grid = uint64_t(tilesY) * A.tilesX;
             B200_REQUIRE(grid <= 0x7fffffffull, B200_ERANGE);
             auto const s = reinterpret_cast<cudaStream_t>(stream);
+            if(walk)
+                return launchWalk(plan, s, src_index, A, levels, rx == ry && b200::tune("heat.stepn_sq", 1) != 0);
             size_t const smemBytes = size_t(boxX) * size_t(tyt + 2 * levels) * 8;
             auto launch = [&](auto* kernel, int threads) { kernel<<<unsigned(grid), threads, smemBytes, s>>>(plan->mapN[src_index], A); };
             // square cells (dx == dy): rX == rY bit for bit, one product serves both directions (makeRowN<SQ>)
@@ -1590,7 +2157,7 @@ extern "C"
         double const* time_factors)
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors, B200_EINVAL);
-        B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
+        B200_REQUIRE(levels == 3 || levels == 4 || levels == 6 || levels == 8, B200_EINVAL);
         B200_REQUIRE(plan->edges == B200_EDGE_ALL && !plan->hasHalo && plan->padY == 1, B200_EINVAL);
         return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, 0);
     }
@@ -1606,7 +2173,7 @@ extern "C"
         uint32_t step)
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors && step >= 1, B200_EINVAL);
-        B200_REQUIRE(levels == 3 || levels == 4, B200_EINVAL);
+        B200_REQUIRE(levels == 3 || levels == 4 || levels == 6 || levels == 8, B200_EINVAL);
         // the ghost rows must be at least as deep as the launch advances (all of them are refreshed by every launch)
         B200_REQUIRE(plan->hasHalo && plan->padY >= uint32_t(levels), B200_EINVAL);
         return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, step);

@@ -39,11 +39,11 @@ namespace
     };
 
     // HINT: 0 = default cache policy, 1 = streaming loads (ld.nc.L1::no_allocate) AND streaming stores (st.cs),
-    //       2 = streaming loads only, 3 = streaming stores only
+    //       2 = streaming loads only, 3 = streaming stores only, 4 = as 1 with L2::evict_last on the (256-bit) loads
     template<int HINT>
-    inline constexpr int kLoadHint = (HINT == 1 || HINT == 2) ? 1 : 0;
+    inline constexpr int kLoadHint = HINT == 4 ? 2 : ((HINT == 1 || HINT == 2) ? 1 : 0);
     template<int HINT>
-    inline constexpr int kStoreHint = (HINT == 1 || HINT == 3) ? 1 : 0;
+    inline constexpr int kStoreHint = (HINT == 1 || HINT == 3 || HINT == 4) ? 1 : 0;
 
     template<int HINT, typename T, int VB>
     __device__ __forceinline__ Pack<T, VB> loadPack(T const* base, uint64_t vecIdx)
@@ -351,20 +351,24 @@ namespace
     // reproducible to 1 GB/s): a CTA that owns 32 KB of every array beats the 16 KB one of round 1 --
     //   Triad (two loads in flight per vector)  1024 threads x 1 vector   7130 vs 7089 GB/s
     //   Copy  (one load per vector)              256 threads x 4 vectors  7098 vs 6994 GB/s
-    // Add follows Triad, Mul follows Copy; Init (stores only, 7.59 TB/s) and Nstream keep 512 x 1.
+    //   Mul   (one load, four DMUL per vector)  1024 threads x 1 vector   7094 vs 6887 GB/s at Copy's shape -- wherever
+    //         the two arrays lie (profiles/r02/tune_mul.log, placement.log: the deficit is the shape, not the placement)
+    // Add follows Triad; Init (stores only, 7.59 TB/s) and Nstream keep 512 x 1.
     struct ShapeDefault
     {
-        int unroll, block;
+        int unroll, block, hint;
     };
 
     ShapeDefault shapeDefault(char const* opName)
     {
         std::string const op(opName);
         if(op == "triad" || op == "add")
-            return {1, 1024};
-        if(op == "copy" || op == "mul")
-            return {4, 256};
-        return {1, 512};
+            return {1, 1024, 4}; // two load streams: L2::evict_last on the loads (+0.3 %)
+        if(op == "mul")
+            return {1, 1024, 1};
+        if(op == "copy")
+            return {4, 256, 1};
+        return {1, 512, 1};
     }
 
     StreamCfg streamCfg(char const* opName, int elemBytes)
@@ -375,7 +379,7 @@ namespace
         ShapeDefault const d = shapeDefault(opName);
         c.vb = int(b200::tune((p + "vb").c_str(), b200::tune("stream.vb", 32)));
         c.unroll = int(b200::tune((p + "unroll").c_str(), b200::tune("stream.unroll", d.unroll)));
-        c.hint = int(b200::tune((p + "hint").c_str(), b200::tune("stream.hint", 1)));
+        c.hint = int(b200::tune((p + "hint").c_str(), b200::tune("stream.hint", d.hint)));
         c.block = int(b200::tune((p + "block").c_str(), b200::tune("stream.block", d.block)));
         c.ctasPerSm = int(b200::tune((p + "ctas_per_sm").c_str(), b200::tune("stream.ctas_per_sm", 0)));
         return c;
@@ -433,8 +437,8 @@ namespace
             vb = 16;
         if(vb == 16 && !aligned16)
             vb = int(sizeof(T));
-        if(cfg.hint < 0 || cfg.hint > 3)
-            return b200::fail(B200_EINVAL, "stream.hint must be 0..3", __FILE__, __LINE__);
+        if(cfg.hint < 0 || cfg.hint > 4)
+            return b200::fail(B200_EINVAL, "stream.hint must be 0..4", __FILE__, __LINE__);
         if(vb == 32)
         {
             switch(cfg.hint)
@@ -445,8 +449,10 @@ namespace
                 return launchUnroll<Op, T, 32, 1>(s, op, n, cfg);
             case 2:
                 return launchUnroll<Op, T, 32, 2>(s, op, n, cfg);
-            default:
+            case 3:
                 return launchUnroll<Op, T, 32, 3>(s, op, n, cfg);
+            default:
+                return launchUnroll<Op, T, 32, 4>(s, op, n, cfg);
             }
         }
         if(vb == 16)

@@ -177,21 +177,38 @@ def slab_for(rank: int, world: int, NY: int, NX: int, ghost: int) -> Slab:
     return Slab(rank, world, NY // world, NX, ghost, edges, nb)
 
 
+#: time levels one launch can advance: 1 (one-step kernel), 2, 3, 4 (tile kernels), 4, 6, 8 (walker kernel)
+SUPPORTED_DEPTHS = (1, 2, 3, 4, 6, 8)
+
+
 def launch_schedule(n: int, depth: int, min_depth: int = 1) -> list[int]:
-    """Time levels per launch for n steps with at most `depth` levels per launch: greedy, but never a tail shallower
-    than needed (4 = 2 + 2 rather than 3 + 1). min_depth = 2 for slabs, which cannot advance a single level."""
+    """Time levels per launch for n steps with at most `depth` levels per launch, out of the depths the kernels support
+    (SUPPORTED_DEPTHS): the fewest launches, and among those schedules the one whose shallowest launch is deepest
+    (4 = 2 + 2 rather than 3 + 1), deep launches first. min_depth = 2 for slabs, which cannot advance a single level."""
     if n < 0 or depth < max(1, min_depth):
         raise ValueError("launch_schedule: bad arguments")
-    if min_depth > 1 and (n == 1 or (depth == 2 and n % 2 != 0)):
-        raise ValueError(f"{n} step(s) cannot be covered by launches of {min_depth}..{depth} time levels")
-    out, left = [], n
-    while left > 0:
-        k = min(depth, left)
-        if k > 2 and left - k == 1:
-            k -= 1
-        out.append(k)
-        left -= k
-    return out
+    allowed = [d for d in SUPPORTED_DEPTHS if min_depth <= d <= depth]
+    if not allowed:
+        raise ValueError(f"no supported launch depth in {min_depth}..{depth}")
+    top = allowed[-1]
+    bulk = max(0, (n - 4 * top) // top)  # whole launches of the deepest kind; the tail is planned exactly
+    m = n - bulk * top
+    # best[k] = (launches, -shallowest, first depth) for k steps, or None
+    best: list = [None] * (m + 1)
+    best[0] = (0, -top, 0)
+    for k in range(1, m + 1):
+        for d in allowed:
+            if d <= k and best[k - d] is not None:
+                cand = (best[k - d][0] + 1, max(best[k - d][1], -d), d)
+                if best[k] is None or cand[:2] < best[k][:2]:
+                    best[k] = cand
+    if best[m] is None:
+        raise ValueError(f"{n} step(s) cannot be covered by launches of {allowed} time levels")
+    tail, k = [], m
+    while k > 0:
+        tail.append(best[k][2])
+        k -= best[k][2]
+    return [top] * bulk + sorted(tail, reverse=True)
 
 
 def combine_in_rank_order(parts):

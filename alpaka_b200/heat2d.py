@@ -90,19 +90,27 @@ class Heat2D:
         self.queue.wait()
         self.cur = 0
 
-    #: time levels per launch that `step(n, fuse=True)` aims for (1..4); tests and tools override it per call
-    DEFAULT_FUSE = 4  # measured at 16384^2, cold burst / the full 1000 steps under the power cap, us per step:
-    #                   1 -> 624 / 672, 2 -> 328 / 372, 3 -> 220 / 241, 4 -> 199 / 221 (profiles/r01/heat_cold_probe.log)
+    #: time levels per launch that `step(n, fuse=True)` aims for (decomp.SUPPORTED_DEPTHS); tests and tools override it per call.
+    #: Measured over ~1000 steps under the power cap, us per step (profiles/r02/heat_depth_probe.log, heat_walk_probe.log):
+    #:   16384^2      tile kernel 4 levels 204-215 | walker 4 levels 186-195, 6 levels 182-189, 8 levels 174-185
+    #:   2048 x 16384 tile kernel 4 levels 28.5    | walker 4 levels 26.1-26.7, 6 levels 29.0-29.5, 8 levels 36-39
+    #: -> four levels by default, eight on fields tall enough for long walks (DEEP_FUSE from DEEP_MIN_ROWS rows on)
+    DEFAULT_FUSE = 4
+    DEEP_FUSE = 8
+    DEEP_MIN_ROWS = 12288
+
+    def default_depth(self) -> int:
+        return self.DEEP_FUSE if self.ny >= self.DEEP_MIN_ROWS and self.nx >= 4096 else self.DEFAULT_FUSE
 
     def step(self, n: int = 1, *, fuse=True) -> None:
-        """n FTCS steps. `fuse` (stand-alone fields): up to `fuse` steps (True = DEFAULT_FUSE, False = 1) go through ONE
+        """n FTCS steps. `fuse` (stand-alone fields): up to `fuse` steps (True = default_depth(), False = 1) go through ONE
         launch that keeps the intermediate time levels in registers -- b200_heat2d_step2_f64 (2 levels) or
-        b200_heat2d_stepn_f64 (3, 4): HBM traffic of one step, same bits. A remainder runs in shallower launches.
+        b200_heat2d_stepn_f64 (3, 4, 6, 8): HBM traffic of one step, same bits. A remainder runs in shallower launches.
         NB after a fused launch the current field is in the buffer one swap away, whatever the number of levels."""
         lib = _lib.load()
-        depth = self.DEFAULT_FUSE if fuse is True else (1 if fuse is False else int(fuse))
-        if not 1 <= depth <= 4:
-            raise B200Error(-1, "heat2d: between 1 and 4 time levels per launch")
+        depth = self.default_depth() if fuse is True else (1 if fuse is False else int(fuse))
+        if not 1 <= depth <= 8:
+            raise B200Error(-1, "heat2d: between 1 and 8 time levels per launch")
         if self.edges != EDGE_ALL:
             depth = 1
         from .decomp import launch_schedule

@@ -169,8 +169,8 @@ class HeatSlab(_HaloWiring):
         import math
 
         G = self.DEFAULT_LEVELS if levels is None else int(levels)
-        if G not in (2, 3, 4):
-            raise B200Error(-1, "heat slabs advance 2, 3 or 4 time levels per launch")
+        if G not in (2, 3, 4, 6, 8):
+            raise B200Error(-1, "heat slabs advance 2, 3, 4, 6 or 8 time levels per launch")
         try:
             self.tile = decomp.slab_for(rank, world, NY, NX, G)  # geometry: pure host logic, tested on CPU
         except ValueError as e:

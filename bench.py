@@ -647,13 +647,15 @@ def run_ours(args):
         NY = NX = args.heat or 16384
 
         def fp64_view(entry, levels, cells, ms_launch, clk):
-            """The fused launches are bound by the FP64 pipe, not by HBM: algorithmic DP instructions (3 mul + 4 add per cell
-            and level, every product shared by the two cells that use it) over the pipe's issue rate at the clock seen."""
+            """The fused launches are bound by the FP64 pipe and the issue slots next to HBM: algorithmic DP instructions (on
+            square cells 2 mul + 4 add per cell and level, every product shared by the cells that use it) over the pipe's
+            issue rate at the clock seen."""
             mhz = (clk or {}).get("sm_mhz") or 1965.0
             rate = 148 * FP64_LANES_PER_SM_CLK * mhz * 1e6
-            entry["fp64_pipe_frac"] = round(7.0 * cells * levels / (ms_launch * 1e-3) / rate, 4)
-            entry["fp64_pipe_note"] = (f"7 DP instr per cell and level (algorithmic minimum) / (148 SMs x 64 lanes x {mhz:.0f} MHz); the kernel "
-                                       "executes about 1.45x that (halo columns/rows recomputed, profiles/r02)")
+            entry["fp64_pipe_frac"] = round(6.0 * cells * levels / (ms_launch * 1e-3) / rate, 4)
+            entry["fp64_pipe_note"] = (f"6 DP instr per cell and level (algorithmic minimum, square cells) / (148 SMs x 64 lanes x {mhz:.0f} MHz); "
+                                       "executed: x 128/120 (4 levels; 128/112 at 6, 8) columns a warp window gives up, x (rows + 2 levels)/rows per "
+                                       "walker segment; the tile kernels (2, 3 levels, heat.walk=0) about 1.45 x (profiles/r02)")
 
         if world == 1:
             dx, dy = 1.0 / (NX + 1), 1.0 / (NY + 1)
@@ -667,15 +669,22 @@ def run_ours(args):
             record("heat2d_f64", timed(lambda: h.step(1), max(20, K), 5), 16.0 * NY * NX)
             # 2, 3 and 4 time levels per launch (b200_heat2d_step2_f64 / b200_heat2d_stepn_f64): the same 16 B per cell per
             # step of ALGORITHMIC bytes, a half / a third / a quarter of them actually moved, so the fraction of the HBM peak exceeds 1
-            for G in (4, 3, 2):  # the default depth first, on a board that is still cool
+            D = h.default_depth()  # 8 at 16384^2 (walker kernel), see alpaka_b200/heat2d.py
+            for G in (8, 6, 4, 3, 2):  # walker kernel (8, 6, 4), tile kernels (3, 2)
                 kG = record(f"heat2d_f64_{G}_steps_per_launch", timed(lambda: h.step(G, fuse=G), max(20, K), 5), G * 16.0 * NY * NX)
                 kG["ms_per_step"] = round(kG["ms"] / G, 4)
+                kG["kernel"] = "heatWalkKernel" if G in (4, 6, 8) else ("heatStepNKernel" if G == 3 else "heatStep2Kernel")
                 # what one launch actually moves: one read + one write of the field (ncu: 4.25 GB at 16384^2), whatever G
                 kG["hbm_pass_gbs"] = round(16.0 * NY * NX * 1e-9 / (kG["ms"] * 1e-3), 1)
                 kG["hbm_pass_frac_of_peak"] = round(kG["hbm_pass_gbs"] / peak, 4)
                 fp64_view(kG, G, NY * NX, kG["ms"], None)
+            # the round-1 tile kernel at four levels, for the record (heat.walk = 0)
+            ab.runtime.tune_set("heat.walk", 0)
+            kT = record("heat2d_f64_4_steps_per_launch_tile_kernel", timed(lambda: h.step(4, fuse=4), max(20, K), 5), 4 * 16.0 * NY * NX)
+            kT.update(ms_per_step=round(kT["ms"] / 4, 4), kernel="heatStepNKernel<4>")
+            ab.runtime.tune_set("heat.walk", 1)
             # BASELINE.json configs[3] as specified: 1000 FTCS steps in one go (sustained clocks, not a short burst)
-            for G in (() if args.no_sustained else (1, 4)):
+            for G in (() if args.no_sustained else (1, D)):
                 ms_step, clk = timed_run(lambda: h.step(1000, fuse=G), 1000)
                 kS = record(f"heat2d_f64_1000_steps_{G}_per_launch", ms_step, 16.0 * NY * NX)
                 kS.update(sustained=True, ms_per_step=round(ms_step, 4), clocks=clk)
@@ -698,7 +707,7 @@ def run_ours(args):
                 e2e_paths["heat2d_f64_1000_steps"] = {
                     "gbs": round(16.0 * NY * NX * 1000 * 1e-9 / t_e, 1), "seconds": round(t_e, 4), "h2d_bytes": fb, "d2h_bytes": fb,
                     "max_abs_error_vs_analytic": err,
-                    "how": "pinned host field -> H2D -> 1000 FTCS steps (4 levels per launch) -> D2H, wall clock (heatEquation2D.cpp:88-190)"}
+                    "how": f"pinned host field -> H2D -> 1000 FTCS steps ({D} levels per launch) -> D2H, wall clock (heatEquation2D.cpp:88-190)"}
             h.close()
             del hfield
         else:

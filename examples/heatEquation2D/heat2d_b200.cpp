@@ -10,10 +10,10 @@
 //                     ALPAKA_B200_NATIVE=0)
 //   --mode=fused      per step: one launch of the fused native kernel (alpaka::b200::Heat2DStepper)
 //   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
-//   --mode=fused3 / fused4   per THREE / FOUR steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
+//   --mode=fused3 / fused4 / fused6 / fused8   per THREE / FOUR / SIX / EIGHT steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
 //                     a remainder runs in shallower launches); same bits
 //   --mode=slabs      --slabs=K row slabs of the field in this process, slab k on device k % (number of devices), --levels=G
-//                     (2..4) time levels per launch and per ghost-row exchange (alpaka::b200::Heat2DSlabs); same bits
+//                     (2, 3, 4, 6, 8) time levels per launch and per ghost-row exchange (alpaka::b200::Heat2DSlabs); same bits
 //   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
 //   --output=<file>   dump the final (ny+2) x (nx+2) field, unpadded, for the parity tests
 #include "../common/cli.hpp"
@@ -94,9 +94,11 @@ auto main(int argc, char** argv) -> int
             alpaka::memcpy(computeQueue, uNextBufAcc, uBufHost);
             alpaka::wait(computeQueue);
         };
-        if(mode == "fused" || mode == "fused2" || mode == "fused3" || mode == "fused4")
+        auto const depthOf = [](std::string const& m) { return m == "fused" ? 1 : (m.size() == 6 ? m[5] - '0' : 0); };
+        bool const fusedN = mode == "fused2" || mode == "fused3" || mode == "fused4" || mode == "fused6" || mode == "fused8";
+        if(mode == "fused" || fusedN)
         {
-            int const depth = mode == "fused" ? 1 : (mode == "fused2" ? 2 : (mode == "fused3" ? 3 : 4));
+            int const depth = depthOf(mode);
             {
                 alpaka::b200::Heat2DStepper warm(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
                 warm.steps(computeQueue, static_cast<uint32_t>(depth), depth);
@@ -170,9 +172,9 @@ auto main(int argc, char** argv) -> int
             if(stepper.currentIndex() == 1)
                 std::swap(uNextBufAcc, uCurrBufAcc);
         }
-        else if(mode == "fused2" || mode == "fused3" || mode == "fused4")
+        else if(fusedN)
         {
-            int const depth = mode == "fused2" ? 2 : (mode == "fused3" ? 3 : 4);
+            int const depth = depthOf(mode);
             alpaka::b200::Heat2DStepper stepper(uCurrBufAcc, uNextBufAcc, dx, dy, dt);
             t0 = std::chrono::high_resolution_clock::now();
             stepper.steps(computeQueue, numTimeSteps, depth);

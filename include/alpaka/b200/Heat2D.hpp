@@ -16,6 +16,23 @@
 #include <string>
 #include <vector>
 
+    //! Time levels of the next launch when `n` steps are left and a launch may advance up to `depth`: the deepest depth
+    //! the kernels support (1, 2, 3 tile kernels; 4, 6, 8 walker kernel) that does not leave a single step behind
+    //! (4 = 2 + 2 rather than 3 + 1); `minDepth` = 2 for slabs. 0 if nothing fits.
+    [[nodiscard]] inline auto heatNextDepth(std::uint32_t n, int depth, int minDepth = 1) -> std::uint32_t
+    {
+        for(int k : {8, 6, 4, 3, 2, 1})
+        {
+            if(k > depth || k < minDepth || static_cast<std::uint32_t>(k) > n)
+                continue;
+            std::uint32_t const left = n - static_cast<std::uint32_t>(k);
+            if(left == 1 && (k > 2 || minDepth > 1))
+                continue;
+            return static_cast<std::uint32_t>(k);
+        }
+        return 0;
+    }
+
 namespace alpaka::b200
 {
     class Heat2DStepper
@@ -98,14 +115,14 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
-        //! `levels` (3 or 4) fused steps in ONE launch (b200_heat2d_stepn_f64: own column pair per thread and level, the
-        //! horizontal neighbours by warp shuffle); same bits, the roles of the buffers swap ONCE.
+        //! `levels` (3, 4, 6 or 8) fused steps in ONE launch (b200_heat2d_stepn_f64: own column pair per thread and level, the
+        //! horizontal neighbours by warp shuffle; 4, 6, 8: the walker kernel); same bits, the roles of the buffers swap ONCE.
         template<typename TQueue>
         void stepN(TQueue& queue, int levels)
         {
             constexpr double pi = math::constants::pi;
-            double tf[4] = {};
-            for(int l = 0; l < levels && l < 4; ++l)
+            double tf[8] = {};
+            for(int l = 0; l < levels && l < 8; ++l)
                 tf[l] = std::exp(-pi * pi * ((m_step + 1u + static_cast<std::uint32_t>(l)) * m_dt));
             check(b200_heat2d_stepn_f64(m_plan, queue.getNativeHandle(), m_cur, m_rX, m_rY, levels, tf));
             m_step += static_cast<std::uint32_t>(levels);
@@ -113,18 +130,16 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
-        //! `n` steps with up to `depth` (1..4; measured best: 4) time levels per launch; a remainder runs in shallower
+        //! `n` steps with up to `depth` (1..8) time levels per launch; a remainder runs in shallower
         //! launches (4 = 2 + 2 rather than 3 + 1)
         template<typename TQueue>
         void steps(TQueue& queue, std::uint32_t n, int depth = 4)
         {
-            if(depth < 1 || depth > 4)
-                throw std::runtime_error("Heat2DStepper::steps: between 1 and 4 time levels per launch");
+            if(depth < 1 || depth > 8)
+                throw std::runtime_error("Heat2DStepper::steps: between 1 and 8 time levels per launch");
             while(n > 0)
             {
-                auto k = static_cast<std::uint32_t>(depth) < n ? static_cast<std::uint32_t>(depth) : n;
-                if(k > 2 && n - k == 1)
-                    --k;
+                auto const k = heatNextDepth(n, depth);
                 if(k == 1)
                     step(queue);
                 else if(k == 2)
@@ -178,8 +193,8 @@ namespace alpaka::b200
             , m_rY(dt / (dy * dy))
         {
             auto const K = static_cast<Idx>(devs.size());
-            if(K == 0 || levels < 2 || levels > 4 || NY % K != 0 || NY / K < 2 * m_G)
-                throw std::runtime_error("Heat2DSlabs: NY must divide into slabs of at least 2*levels rows, levels in 2..4");
+            if(K == 0 || !(levels == 2 || levels == 3 || levels == 4 || levels == 6 || levels == 8) || NY % K != 0 || NY / K < 2 * m_G)
+                throw std::runtime_error("Heat2DSlabs: NY must divide into slabs of at least 2*levels rows, levels 2, 3, 4, 6 or 8");
             m_ny = NY / K;
             bool distinct = false;
             for(auto const& d : devs)
@@ -267,10 +282,10 @@ namespace alpaka::b200
             constexpr double pi = math::constants::pi;
             while(n > 0)
             {
-                auto k = m_G < n ? m_G : n;
-                if(n - k == 1)
-                    --k;
-                double tf[4] = {};
+                auto const k = heatNextDepth(n, static_cast<int>(m_G), 2);
+                if(k == 0)
+                    throw std::runtime_error("Heat2DSlabs::steps: the remaining steps cannot be covered");
+                double tf[8] = {};
                 for(Idx l = 0; l < k; ++l)
                     tf[l] = std::exp(-pi * pi * ((m_step + 1u + l) * m_dt));
                 ++m_launch;

@@ -341,10 +341,12 @@ extern "C"
      * level is unchanged, so the field is bit-identical to two b200_heat2d_step_f64 calls. Stand-alone fields only
      * (plan `edges` == B200_EDGE_ALL, no halo): a decomposed tile would need ghost cells two deep. */
     int b200_heat2d_step2_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor_1, double time_factor_2);
-    /* `levels` (3 or 4) steps in one launch: deeper temporal blocking. Threads compute only their own column pair per level and
-     * take the horizontal neighbours from adjacent lanes by warp shuffle (no recomputation, no shared-memory round trip);
+    /* `levels` (3, 4, 6 or 8) steps in one launch: deeper temporal blocking. Threads compute only their own column pair per level
+     * and take the horizontal neighbours from adjacent lanes by warp shuffle (no recomputation, no shared-memory round trip);
      * time_factors[l] is the boundary factor of the l-th level of the launch (time_factors[levels-1] the result's).
-     * Same conditions and the same bit-identical result as b200_heat2d_step2_f64. */
+     * levels = 3: tiles of rows; levels = 4, 6, 8: one warp WALKS down a 64-column window over a tall row segment and keeps
+     * every level as partial sums in registers, so no row is loaded or recomputed twice (heatWalkKernel; tunables heat.walk,
+     * heat.walk_shape, heat.walk_seg_rows). Same conditions and the same bit-identical result as b200_heat2d_step2_f64. */
     int b200_heat2d_stepn_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors);
     /* Restrict a step to a row/column window of OUTPUT cells [j0,j1) x [i0,i1) in padded coordinates
      * (used to split interior / edge strips for halo overlap). */
@@ -372,7 +374,7 @@ extern "C"
     } b200_heat2d_halo;
     int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo);
     int b200_heat2d_step_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor, uint32_t step);
-    /* ---- Row-SLAB decomposition with G = 2, 3 or 4 time levels per launch and per exchange (new). Temporal blocking
+    /* ---- Row-SLAB decomposition with G = 2 .. 8 time levels per launch and per exchange (new). Temporal blocking
      * needs ghost cells G deep; with row slabs (every rank keeps the full width) only rows are exchanged, they are
      * contiguous, and no diagonal neighbour exists. Array layout of a slab: (ny+2G) x (nx+2) doubles -- rows 0..G-1 and
      * ny+G..ny+2G-1 are ghost rows on a side with a neighbour; on a physical side row G-1 / ny+G is the ring and the rows
@@ -380,7 +382,7 @@ extern "C"
      * entries (sy[j] for local row j, ghost rows included: their ring-column cells are boundary cells of the
      * neighbour's rows). `edges` must contain LEFT and RIGHT; ny >= 2G; all slabs of a field have the same ny, nx, pitch.
      * b200_heat2d_plan_set_halo wires the neighbours (sides 0 = top, 1 = bottom; left/right stay NULL). One launch of
-     * b200_heat2d_step2_halo_f64 (2 levels) / b200_heat2d_stepn_halo_f64 (levels = 3 or 4), levels <= G, reads level s
+     * b200_heat2d_step2_halo_f64 (2 levels) / b200_heat2d_stepn_halo_f64 (levels = 3, 4, 6 or 8), levels <= G, reads level s
      * (ghost rows included) from buffer `src_index`, writes level s+levels of the core rows and physical ring into the
      * other buffer, stores its first / last G core rows straight into the neighbours' ghost rows (peer stores from
      * registers; always all G, so launches of different depths can follow each other, e.g. 1000 = 332 x 3 + 2 x 2) and

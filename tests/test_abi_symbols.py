@@ -78,11 +78,11 @@ def test_argument_validation_of_the_fused_entries_needs_no_device():
     assert lib.b200_heat2d_stepn_f64(None, None, 0, 0.1, 0.1, 3, tf) == EINVAL
     assert lib.b200_heat2d_step2_halo_f64(None, None, 0, 0.1, 0.1, 1.0, 1.0, 1) == EINVAL
     assert lib.b200_heat2d_stepn_halo_f64(None, None, 0, 0.1, 0.1, 4, tf, 1) == EINVAL
-    # a slab keeps the full width (LEFT | RIGHT physical), at least 2 * ghost rows, ghost depth 2..4
+    # a slab keeps the full width (LEFT | RIGHT physical), at least 2 * ghost rows, ghost depth 2..8
     sx, sy = np.zeros(66), np.zeros(72)
     plan = ctypes.c_void_p()
     fake = ctypes.c_void_p(256)  # never dereferenced: the checks below fail first
-    for edges, ny, ghost in ((1 | 2, 64, 2), (4 | 8, 3, 2), (4 | 8, 64, 1), (4 | 8, 64, 5)):
+    for edges, ny, ghost in ((1 | 2, 64, 2), (4 | 8, 3, 2), (4 | 8, 64, 1), (4 | 8, 64, 9)):
         rc = lib.b200_heat2d_slab_plan_create(0, fake, fake, 66 * 8 + 16, ny, 64, sx.ctypes.data, sy.ctypes.data, edges, ghost,
                                               ctypes.byref(plan))
         assert rc == EINVAL, (edges, ny, ghost, rc)

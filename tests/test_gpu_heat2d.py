@@ -31,11 +31,11 @@ def _init(ny, nx, dx, dy):
 SHAPES = [(64, 64), (1, 1), (1, 7), (9, 1), (16, 16), (33, 129), (31, 127), (100, 257), (256, 1024), (515, 1030)]
 
 
-@pytest.mark.parametrize("fuse", [1, 2, 3, 4], ids=lambda k: f"{k}_levels_per_launch")
+@pytest.mark.parametrize("fuse", [1, 2, 3, 4, 6, 8], ids=lambda k: f"{k}_levels_per_launch")
 @pytest.mark.parametrize("shape", SHAPES)
 def test_heat2d_bit_exact_vs_oracle(gpu, shape, fuse):
     """25 steps: 25 one-step launches; 12 two-level launches (b200_heat2d_step2_f64) + 1; 8 three-level launches
-    (b200_heat2d_stepn_f64) + 1; 6 four-level launches + 1."""
+    (b200_heat2d_stepn_f64) + 1; 6 four-level launches + 1; 6 + 6 + 6 + 4 + 3; 8 + 8 + 6 + 3 (4, 6, 8: the walker kernel)."""
     ab, dev, queue = gpu
     ny, nx = shape
     dx, dy, dt = ol.heat_params(ny, nx)
@@ -79,11 +79,39 @@ def test_heat2d_n_level_kernel_every_tile_shape(gpu, cfg):
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
     ab.runtime.tune_set("heat.stepn_rpt", rpt)
     ab.runtime.tune_set("heat.stepn_nwy", nwy)
+    ab.runtime.tune_set("heat.walk", 0)  # four levels: the tile kernel, not the walker that replaced it as the default
     try:
         got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
     finally:
         ab.runtime.tune_set("heat.stepn_rpt", 16)
         ab.runtime.tune_set("heat.stepn_nwy", 2)
+        ab.runtime.tune_set("heat.walk", 1)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("seg_rows", [0, 40, 7], ids=lambda r: f"seg{r}")
+@pytest.mark.parametrize("shape_key", [43, 44, 46, 26], ids=lambda k: f"R{k // 10}_stages{k % 10}")
+@pytest.mark.parametrize("levels", [4, 6, 8])
+@pytest.mark.parametrize("square", [False, True], ids=["rx_ne_ry", "square_cells"])
+def test_heat2d_walker_kernel_every_shape(gpu, square, levels, shape_key, seg_rows):
+    """Every instantiation of the walker kernel (heatWalkKernel: one warp walks down a 128-column window, levels kept as
+    partial sums in registers) on a rough field: partial windows on the right edge, several row segments per window
+    (heat.walk_seg_rows forces short ones, down to segments shorter than the 2S-row prologue), chunk counts that do not
+    divide the stage ring, both product forms (square cells share v*rX). Bit-exact against the oracle, ring included."""
+    ab, dev, queue = gpu
+    ny, nx = (333, 333) if square else (203, 391)
+    dx, dy, dt = ol.heat_params(ny, nx)
+    assert (dt / (dx * dx) == dt / (dy * dy)) == square
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=24).reshape(ny + 2, nx + 2)
+    steps = 2 * levels
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    ab.runtime.tune_set("heat.walk_shape", shape_key)
+    ab.runtime.tune_set("heat.walk_seg_rows", seg_rows)
+    try:
+        got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
+    finally:
+        ab.runtime.tune_set("heat.walk_shape", 0)
+        ab.runtime.tune_set("heat.walk_seg_rows", 0)
     assert got.tobytes() == want.tobytes()
 
 
@@ -103,11 +131,32 @@ def test_heat2d_n_level_kernel_square_cells(gpu, levels, variant):
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
     for k, v in variant.items():
         ab.runtime.tune_set(k, v)
+    ab.runtime.tune_set("heat.walk", 0)  # the tile kernel (the walker has its own test above)
     try:
         got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
     finally:
-        for k, v in {"heat.stepn_sq": 1, "heat.stepn_ctas": 4, "heat.stepn_rpt": 16, "heat.stepn_nwy": 2}.items():
+        for k, v in {"heat.stepn_sq": 1, "heat.stepn_ctas": 4, "heat.stepn_rpt": 16, "heat.stepn_nwy": 2, "heat.walk": 1}.items():
             ab.runtime.tune_set(k, v)
+    assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("levels,minb", [(4, 4), (4, 3), (6, 3), (6, 2), (8, 3), (8, 2)], ids=lambda v: str(v))
+def test_heat2d_walker_kernel_register_budgets(gpu, levels, minb):
+    """Both register budgets of every depth (heat.walk_minb: CTAs per SM the allocation is held to) on a field wide enough
+    for interior windows (the bare path), misaligned tail windows and several segments."""
+    ab, dev, queue = gpu
+    ny, nx = 150, 700
+    dx, dy, dt = ol.heat_params(ny, nx)
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=25).reshape(ny + 2, nx + 2)
+    steps = levels + 4
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    ab.runtime.tune_set("heat.walk_minb", minb)
+    ab.runtime.tune_set("heat.walk_seg_rows", 48)
+    try:
+        got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
+    finally:
+        ab.runtime.tune_set("heat.walk_minb", 0)
+        ab.runtime.tune_set("heat.walk_seg_rows", 0)
     assert got.tobytes() == want.tobytes()
 
 

@@ -85,7 +85,7 @@ def test_single_tile_halo_launch_equals_plain_step(gpu):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# Row slabs advanced 2, 3 or 4 time levels per launch and per exchange (b200_heat2d_step2_halo_f64 /
+# Row slabs advanced 2, 3, 4, 6 or 8 time levels per launch and per exchange (b200_heat2d_step2_halo_f64 /
 # b200_heat2d_stepn_halo_f64): ghost rows as deep as the launch advances.
 def run_slabs(ab, dev, NY, NX, world, steps, u0, levels):
     from alpaka_b200 import multi
@@ -96,13 +96,9 @@ def run_slabs(ab, dev, NY, NX, world, steps, u0, levels):
     for r in runners:
         r.upload(r.window(u0))
     # launch by launch on every slab in turn (they wait for each other's flags); `sched` = steps per round
-    sched, left = [], steps
-    while left > 0:
-        k = min(levels, left)
-        if left - k == 1:
-            k -= 1
-        sched.append(k)
-        left -= k
+    from alpaka_b200 import decomp
+
+    sched = decomp.launch_schedule(steps, levels, min_depth=2)
     assert sum(sched) == steps and all(2 <= k <= levels for k in sched)
     for k in sched:
         for r in runners:
@@ -124,12 +120,12 @@ SLAB_CASES = [(2, 20, 96), (3, 61, 200), (2, 127, 391), (4, 200, 700), (1, 150, 
               (2, 128, 256), (4, 75, 300)]  # the last two: square cells (NY == NX), the shared-product kernel
 
 
-@pytest.mark.parametrize("levels", [2, 3, 4])
+@pytest.mark.parametrize("levels", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("case", SLAB_CASES, ids=lambda c: f"{c[0]}slabs_of_{c[1]}x{c[2]}")
 def test_slabs_fused_levels_equal_undecomposed(gpu, case, levels):
     ab, dev, _ = gpu
     world, ny, NX = case
-    NY, steps = ny * world, 12
+    NY, steps = ny * world, (12 if levels <= 4 else 2 * levels + 4)
     dx, dy, dt = ol.heat_params(NY, NX)
     u0 = np.empty((NY + 2, NX + 2))
     ol.oracle().orc_heat2d_init(P(u0), NY, NX, NX + 2, dx, dy)
@@ -138,11 +134,11 @@ def test_slabs_fused_levels_equal_undecomposed(gpu, case, levels):
     assert got.tobytes() == want.tobytes()
 
 
-@pytest.mark.parametrize("levels", [2, 3, 4])
+@pytest.mark.parametrize("levels", [2, 3, 4, 6, 8])
 def test_slabs_rough_field_bit_exact(gpu, levels):
     """A rough field exercises every neighbour term across the slab borders (the analytic field is smooth)."""
     ab, dev, _ = gpu
-    world, ny, NX, steps = 3, 70, 263, 12
+    world, ny, NX, steps = 3, 70, 263, (12 if levels <= 4 else 2 * levels + 2)
     NY = ny * world
     dx, dy, dt = ol.heat_params(NY, NX)
     u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=33).reshape(NY + 2, NX + 2)
@@ -151,9 +147,10 @@ def test_slabs_rough_field_bit_exact(gpu, levels):
     assert got.tobytes() == want.tobytes()
 
 
-@pytest.mark.parametrize("levels,steps", [(3, 10), (3, 11), (4, 13), (4, 10)])
+@pytest.mark.parametrize("levels,steps", [(3, 10), (3, 11), (4, 13), (4, 10), (6, 17), (8, 21), (8, 13)])
 def test_slabs_mixed_depth_launches(gpu, levels, steps):
-    """A step count that is not a multiple of the ghost depth: shallower launches finish it (3+3+2+2, 3+3+3+2, ...)."""
+    """A step count that is not a multiple of the ghost depth: shallower launches finish it (3+3+2+2, 3+3+3+2, 6+6+3+2,
+    8+8+3+2, 8+3+2 ...; walker and tile kernels mixed on one pair of buffers and one flag protocol)."""
     ab, dev, _ = gpu
     world, ny, NX = 3, 70, 263
     NY = ny * world

@@ -2,6 +2,9 @@
 """Dot with the all-ranks exchange fused into the reduction launch, TWO DEVICES IN ONE PROCESS (plain peer pointers, no
 IPC): the form `ncu` can profile (one process; `--devices 0` captures rank 0's kernel, whose last block stores its scalar
 into device 1's slot array and reads device 1's scalar out of its own) -- NVLink counters of reduceKernel<..., Exchange>.
+Under ncu the profiled device's launches are serialised and replayed, so device 1 is enqueued FIRST (its kernel, not
+profiled, publishes its scalar and then waits for device 0's, which the first replay pass delivers); the flag-wait bound is
+lowered to 5 s so that a mistake here costs seconds of GPU time, not the 60 s default per replay pass.
 
     python tools/exchange_two_devices.py [n]        # n doubles per device (default 2^28)
 """
@@ -34,9 +37,10 @@ def main():
         ab.babelstream.mul(q, a, b)
         bufs.append((a, b))
         outs.append(ab.alloc_buf(d, np.float64, 1, q))
+    ab.runtime.tune_set("exchange.timeout_ms", 5000)
     for call in range(6):
-        for r, q in enumerate(queues):  # enqueue on both devices before waiting on either
-            exs[r].dot_async(q, bufs[r][0], bufs[r][1], outs[r])
+        for r in (1, 0):  # enqueue on both devices before waiting on either; the profiled device last (see above)
+            exs[r].dot_async(queues[r], bufs[r][0], bufs[r][1], outs[r])
         got = []
         for r, q in enumerate(queues):
             h = np.empty(1)
