@@ -10,7 +10,7 @@ What is compared, per world size ("sharded result == un
   dot (integers)   fused exchange on exactly representable data  == the reference DotKernel value bit for bit
   reduce u32/f32   fused exchange (wrap-add / {0,1} data)        == the reference ReduceKernel pair bit for bit
   heat tiles       Py x Px tiles, halo exchange fused into the step kernel, stitched == the undecomposed field
-  heat slabs       row slabs, 2 / 3 / 4 time levels per launch (>= 2 launches of every depth), stitched == the same field
+  heat slabs       row slabs, 2 / 3 / 4 / 6 / 8 time levels per launch (>= 2 launches of every depth), stitched == the same field
 """
 from __future__ import annotations
 
@@ -195,8 +195,8 @@ def check_heat(R: Ranks, G) -> dict:
         if len(R.mine) > 1:
             ab.runtime.tune_set("heat.grid_cap", 0)
 
-    # ---- row slabs, 2 / 3 / 4 levels per launch and per exchange
-    for levels in (2, 3, 4):
+    # ---- row slabs, 2 / 3 / 4 / 6 / 8 levels per launch and per exchange (4, 6, 8: the walker kernel)
+    for levels in (2, 3, 4, 6, 8):
         slabs = {r: multi.HeatSlab(R.queues[r], r, R.world, NY, NX, dt=dt, levels=levels) for r in R.mine}
         R.connect(slabs, exchange=False)
         for r in R.mine:

@@ -104,13 +104,13 @@ def main():
     dist.barrier()
     runner.close()
 
-    # ---- row slabs, 2, 3 and 4 time levels per launch and per exchange (ghost rows that deep), IPC peer pointers
+    # ---- row slabs, 2, 3, 4, 6 and 8 time levels per launch and per exchange (ghost rows that deep), IPC peer pointers
     NYs, NXs, steps2 = 160 * world, 900, 24
     dxs, dys, dts = ol.heat_params(NYs, NXs)
     u0s = np.empty((NYs + 2, NXs + 2))
     ol.oracle().orc_heat2d_init(P(u0s), NYs, NXs, NXs + 2, dxs, dys)
     want_s = ol.orc_heat_run(u0s, 1, steps2, dxs, dys, dts) if rank == 0 else None
-    for levels in (2, 3, 4):
+    for levels in (2, 3, 4, 6, 8):
         slab = multi.HeatSlab(q, rank, world, NYs, NXs, levels=levels)
         multi.connect_over_process_group(slab, dist)
         slab.upload(slab.window(u0s))

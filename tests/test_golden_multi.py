@@ -48,7 +48,7 @@ def test_fixture_sizes_split_over_2_4_8_ranks():
     steps = int(G["heat_params"][3])
     for world in (2, 4, 8):
         decomp.tile_for(world - 1, world, ny, nx)
-        for levels in (2, 3, 4):
+        for levels in (2, 3, 4, 6, 8):
             decomp.slab_for(world - 1, world, ny, nx, levels)
             sched = decomp.launch_schedule(steps, levels, min_depth=2)
             assert sched.count(levels) >= 2, "the fixture must exercise at least two launches of every depth"
