@@ -1171,7 +1171,9 @@ namespace
     constexpr int kWalkWarps = 4; // walkers per CTA
 
     // MINB: CTAs per SM the register allocation is held to (128 threads: 4 -> 128 registers, 3 -> 168, 2 -> 255)
-    template<int S, int R, int ST, bool SQ, int MINB>
+    // SWAP: lanes 4-7, 12-15, ... load the two halves of their quad in the opposite order, which makes both LDS.128 of a row
+    // conflict-free (a 32-byte lane stride is 2-way conflicted otherwise) at the price of four 64-bit selects per row
+    template<int S, int R, int ST, bool SQ, int MINB, bool SWAP = false>
     __global__ void __launch_bounds__(32 * kWalkWarps, MINB) heatWalkKernel(const __grid_constant__ CUtensorMap mapSrc, HeatWArgs const A)
     {
         static_assert(S % 2 == 0 && S >= 2 && S <= kMaxLevels, "even S");
@@ -1276,6 +1278,26 @@ namespace
         uint32_t parity = 0;
         int64_t const pitch = int64_t(A.pitchElems);
         double* outRow = A.dst + int64_t(rowStart - S) * pitch + gi; // output address of the row that input row rowStart completes
+        bool const swapHalves = SWAP && ((lane >> 2) & 1);
+        int const firstHalf = swapHalves ? 2 : 0;
+        auto const loadQuad = [&](double const* q, double (&v)[kWalkCols])
+        {
+            double2 const a = lds128(q + firstHalf), b = lds128(q + (2 - firstHalf));
+            if constexpr(SWAP)
+            {
+                v[0] = swapHalves ? b.x : a.x;
+                v[1] = swapHalves ? b.y : a.y;
+                v[2] = swapHalves ? a.x : b.x;
+                v[3] = swapHalves ? a.y : b.y;
+            }
+            else
+            {
+                v[0] = a.x;
+                v[1] = a.y;
+                v[2] = b.x;
+                v[3] = b.y;
+            }
+        };
         for(int32_t c = 0; c < nChunks; ++c)
         {
             int32_t const r0 = rowStart + c * R; // first input row of the chunk
@@ -1290,8 +1312,8 @@ namespace
 #pragma unroll
                 for(int r = 0; r < R; ++r)
                 {
-                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
-                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    double v[kWalkCols];
+                    loadQuad(rowp + r * BOXX, v);
                     walkRow<S, SQ, kWalkBare>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
                 }
             }
@@ -1301,8 +1323,8 @@ namespace
                 for(int r = 0; r < R; ++r)
                 {
                     double const syNext = syAt(r0 + r); // sy[j0]: the newest entry of the NEXT row's window
-                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
-                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    double v[kWalkCols];
+                    loadQuad(rowp + r * BOXX, v);
                     walkRow<S, SQ, kWalkEdgeCols>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
 #pragma unroll
                     for(int l = S - 1; l > 0; --l)
@@ -1316,8 +1338,8 @@ namespace
                 for(int r = 0; r < R; ++r)
                 {
                     double const syNext = syAt(r0 + r);
-                    double2 const a = lds128(rowp + r * BOXX), b = lds128(rowp + r * BOXX + 2);
-                    double v[kWalkCols] = {a.x, a.y, b.x, b.y};
+                    double v[kWalkCols];
+                    loadQuad(rowp + r * BOXX, v);
                     walkRow<S, SQ, kWalkCareful>(A, st, v, r0 + r, gi, storeLane, ya, yb, outRow + r * pitch, ringMask, validMask, syw);
 #pragma unroll
                     for(int l = S - 1; l > 0; --l)
@@ -1475,14 +1497,14 @@ struct b200_heat2d_plan_st
 namespace
 {
     // ---- the walker form of an S-level launch (heatWalkKernel), S = 4, 6, 8
-    template<int S, int R, int ST, int MINB>
+    template<int S, int R, int ST, int MINB, bool SWAP = false>
     int launchWalkShape(b200_heat2d_plan_t plan, cudaStream_t s, int src_index, HeatWArgs& A, bool sq)
     {
         constexpr int WW = WalkGeom<S>::WW;
         constexpr int BOXX = 32 * kWalkCols;
         constexpr size_t smemBytes = size_t(kWalkWarps) * ST * R * BOXX * 8;
-        auto* const kSq = heatWalkKernel<S, R, ST, true, MINB>;
-        auto* const kGen = heatWalkKernel<S, R, ST, false, MINB>;
+        auto* const kSq = heatWalkKernel<S, R, ST, true, MINB, SWAP>;
+        auto* const kGen = heatWalkKernel<S, R, ST, false, MINB, SWAP>;
         auto* const kernel = sq ? kSq : kGen;
         static std::mutex mtx;
         static int slotsPerSm[2][64] = {}; // [sq][device]: resident walkers per SM (0 = not asked yet)
@@ -1596,16 +1618,24 @@ namespace
             minb = levels == 4 ? 3 : 2;
         auto go = [&]<int S_, int R_, int ST_>() -> int
         {
+            // the default shape also exists with conflict-free loads (heat.walk_lds_swap)
+            bool const swap = R_ == 4 && ST_ == 4 && b200::tune("heat.walk_lds_swap", 0) != 0;
             if constexpr(S_ == 4)
             {
                 if(minb >= 4)
                     return launchWalkShape<S_, R_, ST_, 4>(plan, s, src_index, A, sq);
+                if constexpr(R_ == 4 && ST_ == 4)
+                    if(swap)
+                        return launchWalkShape<S_, R_, ST_, 3, true>(plan, s, src_index, A, sq);
                 return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
             }
             else
             {
                 if(minb >= 3)
                     return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
+                if constexpr(R_ == 4 && ST_ == 4)
+                    if(swap)
+                        return launchWalkShape<S_, R_, ST_, 2, true>(plan, s, src_index, A, sq);
                 return launchWalkShape<S_, R_, ST_, 2>(plan, s, src_index, A, sq);
             }
         };

@@ -126,11 +126,20 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- host / CPU baselines
-def host_threads():
+def _affinity_threads():
     try:
         return len(os.sched_getaffinity(0))
     except Exception:
         return os.cpu_count() or 1
+
+
+# taken once at import: after the reference's OpenMP runtime has started with OMP_PROC_BIND, the calling thread is bound to one
+# core and the affinity mask reads 1
+_HOST_THREADS = _affinity_threads()
+
+
+def host_threads():
+    return _HOST_THREADS
 
 
 def host_mem_available_gb():

@@ -140,10 +140,12 @@ def test_heat2d_n_level_kernel_square_cells(gpu, levels, variant):
     assert got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("swap", [0, 1], ids=["lds_plain", "lds_swapped_halves"])
 @pytest.mark.parametrize("levels,minb", [(4, 4), (4, 3), (6, 3), (6, 2), (8, 3), (8, 2)], ids=lambda v: str(v))
-def test_heat2d_walker_kernel_register_budgets(gpu, levels, minb):
-    """Both register budgets of every depth (heat.walk_minb: CTAs per SM the allocation is held to) on a field wide enough
-    for interior windows (the bare path), misaligned tail windows and several segments."""
+def test_heat2d_walker_kernel_register_budgets(gpu, levels, minb, swap):
+    """Both register budgets of every depth (heat.walk_minb: CTAs per SM the allocation is held to) and both shared-memory
+    load orders (heat.walk_lds_swap: conflict-free LDS.128 with the halves of a quad swapped on every other group of four
+    lanes) on a field wide enough for interior windows (the bare path), misaligned tail windows and several segments."""
     ab, dev, queue = gpu
     ny, nx = 150, 700
     dx, dy, dt = ol.heat_params(ny, nx)
@@ -152,11 +154,13 @@ def test_heat2d_walker_kernel_register_budgets(gpu, levels, minb):
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
     ab.runtime.tune_set("heat.walk_minb", minb)
     ab.runtime.tune_set("heat.walk_seg_rows", 48)
+    ab.runtime.tune_set("heat.walk_lds_swap", swap)
     try:
         got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
     finally:
         ab.runtime.tune_set("heat.walk_minb", 0)
         ab.runtime.tune_set("heat.walk_seg_rows", 0)
+        ab.runtime.tune_set("heat.walk_lds_swap", 0)
     assert got.tobytes() == want.tobytes()
 
 

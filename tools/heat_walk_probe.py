@@ -26,7 +26,7 @@ def t(fn, n):
 
 
 long_steps = int(os.environ.get("LONG_STEPS", "960"))  # a multiple of 2, 3, 4, 6, 8
-RESET = {"heat.walk": 1, "heat.walk_shape": 0, "heat.walk_seg_rows": 0, "heat.walk_minb": 0}
+RESET = {"heat.walk": 1, "heat.walk_shape": 0, "heat.walk_seg_rows": 0, "heat.walk_minb": 0, "heat.walk_lds_swap": 0}
 cases = [("tile  4", 4, {"heat.walk": 0})]
 for S in (4, 6, 8):
     cases.append((f"walk  {S} default", S, {}))
@@ -34,6 +34,9 @@ for S in (4, 6, 8):
     for shape in (43, 44, 46):
         cases.append((f"walk  {S} R{shape // 10}x{shape % 10}", S, {"heat.walk_shape": shape}))
 cases.append(("walk  6 minb3", 6, {"heat.walk_minb": 3}))
+for S in (4, 6, 8, 4, 8):
+    cases.append((f"walk  {S} lds_swap", S, {"heat.walk_lds_swap": 1}))
+    cases.append((f"walk  {S} plain", S, {}))
 for seg in (64, 128, 256, 512):
     for S in (4, 8):
         cases.append((f"walk  {S} seg{seg}", S, {"heat.walk_seg_rows": seg}))
