@@ -990,8 +990,10 @@ namespace
         uint32_t nWin; // column windows
         uint32_t nEdgeRight; // windows at the right end that hold ring columns or columns beyond the field (window 0 is the left one)
         uint32_t nSegAll; // segments per window, strips included
-        uint32_t nStrip; // strip segments at the front of the segment order
-        int32_t stripY0[2], stripY1[2]; // their output rows [y0, y1)
+        uint32_t nFront; // segments at the front of the segment order: slab strips (rows sent to a neighbour) and, when the
+                         // interior runs in the bare-only kernel, the S-row bands next to a physical top / bottom ring
+        uint32_t frontIsStrip; // bit k: front segment k is a strip (flag wait, peer stores, counted for the flag)
+        int32_t frontY0[2], frontY1[2]; // their output rows [y0, y1)
         int32_t intY0, intY1, segRows; // interior output rows [intY0, intY1) in segments of segRows
         uint32_t nWalkers;
         int32_t rows; // rows of the array (sy has that many entries)
@@ -1173,7 +1175,10 @@ namespace
     // MINB: CTAs per SM the register allocation is held to (128 threads: 4 -> 128 registers, 3 -> 168, 2 -> 255)
     // SWAP: lanes 4-7, 12-15, ... load the two halves of their quad in the opposite order, which makes both LDS.128 of a row
     // conflict-free (a 32-byte lane stride is 2-way conflicted otherwise) at the price of four 64-bit selects per row
-    template<int S, int R, int ST, bool SQ, int MINB, bool SWAP = false>
+    // BAREONLY: the interior windows over rows whose every level is a core row, nothing else -- no ring, edge or strip code
+    // in the register allocation (128 registers, a fourth CTA per SM). The full kernel then keeps the edge windows, the
+    // S-row bands next to a physical ring and the strips, and lets this one start next to it (programmatic dependent launch).
+    template<int S, int R, int ST, bool SQ, int MINB, bool SWAP = false, bool BAREONLY = false>
     __global__ void __launch_bounds__(32 * kWalkWarps, MINB) heatWalkKernel(const __grid_constant__ CUtensorMap mapSrc, HeatWArgs const A)
     {
         static_assert(S % 2 == 0 && S >= 2 && S <= kMaxLevels, "even S");
@@ -1186,33 +1191,48 @@ namespace
         uint32_t const walker = blockIdx.x * kWalkWarps + warp;
         if(walker >= A.nWalkers)
             return; // (no CTA-wide barrier anywhere in this kernel)
-        // walker order: the edge windows of every segment first (they run the slower ring-column path; dispatched last they
-        // would be the tail of the launch), then the interior windows segment by segment (strip segments first)
-        uint32_t const nEdge = 1u + A.nEdgeRight, nEdgeWalkers = nEdge * A.nSegAll;
+        uint32_t const nEdge = 1u + A.nEdgeRight;
         uint32_t seg, w;
-        if(walker < nEdgeWalkers)
-        {
-            seg = walker / nEdge;
-            uint32_t const e = walker - seg * nEdge;
-            w = e == 0u ? 0u : A.nWin - e;
-        }
-        else
-        {
-            uint32_t const idx = walker - nEdgeWalkers, nInner = A.nWin - nEdge;
-            seg = idx / nInner;
-            w = 1u + (idx - seg * nInner);
-        }
-        bool const strip = seg < A.nStrip;
+        bool strip = false;
         int32_t ya, yb;
-        if(strip)
+        if constexpr(BAREONLY)
         {
-            ya = A.stripY0[seg];
-            yb = A.stripY1[seg];
+            uint32_t const nInner = A.nWin - nEdge;
+            seg = walker / nInner;
+            w = 1u + (walker - seg * nInner);
+            ya = A.intY0 + int32_t(seg) * A.segRows;
+            yb = min(ya + A.segRows, A.intY1);
         }
         else
         {
-            ya = A.intY0 + int32_t(seg - A.nStrip) * A.segRows;
-            yb = min(ya + A.segRows, A.intY1);
+            // the dependent bare-only launch (if any) may start as soon as every CTA of this grid is under way
+            asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+            // walker order: the edge windows of every segment first (they run the slower ring-column path; dispatched last
+            // they would be the tail of the launch), then the interior windows segment by segment (front segments first)
+            uint32_t const nEdgeWalkers = nEdge * A.nSegAll;
+            if(walker < nEdgeWalkers)
+            {
+                seg = walker / nEdge;
+                uint32_t const e = walker - seg * nEdge;
+                w = e == 0u ? 0u : A.nWin - e;
+            }
+            else
+            {
+                uint32_t const idx = walker - nEdgeWalkers, nInner = A.nWin - nEdge;
+                seg = idx / nInner;
+                w = 1u + (idx - seg * nInner);
+            }
+            if(seg < A.nFront)
+            {
+                strip = (A.frontIsStrip >> seg) & 1u;
+                ya = A.frontY0[seg];
+                yb = A.frontY1[seg];
+            }
+            else
+            {
+                ya = A.intY0 + int32_t(seg - A.nFront) * A.segRows;
+                yb = min(ya + A.segRows, A.intY1);
+            }
         }
         unsigned char* const stages = smem + size_t(warp) * ST * kStageBytes;
         uint64_t* const bar = full[warp];
@@ -1306,8 +1326,8 @@ namespace
             // every row this chunk produces at any level (r0 - S .. r0 + R - 2) is a core row: nothing but the stencil there,
             // except in the ring columns of an edge window. (Rows of the segment's prologue hold finite garbage that no
             // stored cell depends on; the row range [ya, yb) guards the stores.)
-            bool const rowsCore = !strip && r0 - S >= A.loY && r0 + R - 2 <= A.hiY;
-            if(rowsCore && colInterior)
+            bool const rowsCore = BAREONLY || (!strip && r0 - S >= A.loY && r0 + R - 2 <= A.hiY);
+            if(BAREONLY || (rowsCore && colInterior))
             {
 #pragma unroll
                 for(int r = 0; r < R; ++r)
@@ -1361,11 +1381,14 @@ namespace
             }
         }
 
-        if(strip && A.stripCounter != nullptr)
+        if constexpr(!BAREONLY)
         {
-            __syncwarp();
-            if(lane == 0)
-                publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
+            if(strip && A.stripCounter != nullptr)
+            {
+                __syncwarp();
+                if(lane == 0)
+                    publishWhenLastStrip(A.stripCounter, A.stripTiles, A.peerFlag, A.step);
+            }
         }
     }
 
@@ -1497,7 +1520,8 @@ struct b200_heat2d_plan_st
 namespace
 {
     // ---- the walker form of an S-level launch (heatWalkKernel), S = 4, 6, 8
-    template<int S, int R, int ST, int MINB, bool SWAP = false>
+    // SPLIT_OK: this shape also exists as a bare-only kernel for the interior (instantiated for the default shapes only)
+    template<int S, int R, int ST, int MINB, bool SWAP = false, bool SPLIT_OK = false>
     int launchWalkShape(b200_heat2d_plan_t plan, cudaStream_t s, int src_index, HeatWArgs& A, bool sq)
     {
         constexpr int WW = WalkGeom<S>::WW;
@@ -1544,62 +1568,144 @@ namespace
         while(A.nEdgeRight + 1 < A.nWin
               && int64_t(A.nWin - 1 - A.nEdgeRight) * WW - kWalkCols * WalkGeom<S>::LOST + BOXX - 1 > int64_t(plan->nx))
             ++A.nEdgeRight;
-        // output rows: the core rows, plus the ring row on a physical side; strips = the rows sent to a neighbour
-        int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
-        A.nStrip = 0;
-        if(A.ghostTop)
+        // Segments per window for `rowsInt` rows on `slots` resident walkers: maximise (share of the slots used over all
+        // waves) x (share of a walker's rows that are not its 2S-row prologue) x waves / (waves + tail) -- the last factor
+        // models the tail a slower walker of the last wave leaves; it favours a few waves over exactly one.
+        auto const pickSegRows = [&](int64_t rowsInt, int64_t windows, int64_t nslots, double tail) -> int64_t
         {
-            A.stripY0[A.nStrip] = A.loY;
-            A.stripY1[A.nStrip] = A.loY + A.sendRows;
-            outLo = A.loY + A.sendRows;
-            ++A.nStrip;
-        }
-        if(A.ghostBottom)
-        {
-            A.stripY0[A.nStrip] = A.hiY + 1 - A.sendRows;
-            A.stripY1[A.nStrip] = A.hiY + 1;
-            outHi = A.hiY - A.sendRows;
-            ++A.nStrip;
-        }
-        A.intY0 = outLo;
-        A.intY1 = outHi + 1;
-        int64_t const rowsInt = int64_t(A.intY1) - A.intY0;
-        uint32_t nSeg = 0;
-        A.segRows = 1;
-        if(rowsInt > 0)
-        {
-            // Segments per window: maximise (share of the resident-walker slots used over all waves) x (share of a walker's
-            // rows that are not its 2S-row prologue) x waves / (waves + 0.3) -- the last factor models the tail a slower
-            // (edge-window) walker of the last wave leaves; it favours a few waves over exactly one. heat.walk_seg_rows
-            // overrides.
-            int64_t const forced = b200::tune("heat.walk_seg_rows", 0);
             int64_t best = rowsInt;
             double bestScore = -1.0;
-            int64_t const maxSeg = forced > 0 ? 0 : (rowsInt + 15) / 16;
+            int64_t const maxSeg = (rowsInt + 15) / 16;
             for(int64_t k = 1; k <= maxSeg && k <= 8192; ++k)
             {
                 int64_t const segRows = (rowsInt + k - 1) / k;
                 int64_t const segs = (rowsInt + segRows - 1) / segRows;
-                double const walkers = double(segs) * A.nWin;
-                double const waves = double((int64_t(walkers) + slots - 1) / slots);
-                double const score = walkers / (waves * slots) * double(segRows) / double(segRows + 2 * S) * waves / (waves + 0.3);
+                double const walkers = double(segs) * double(windows);
+                double const waves = double((int64_t(walkers) + nslots - 1) / nslots);
+                double const score = walkers / (waves * double(nslots)) * double(segRows) / double(segRows + 2 * S) * waves / (waves + tail);
                 if(score > bestScore + 1e-9)
                 {
                     bestScore = score;
                     best = segRows;
                 }
             }
-            A.segRows = int32_t(forced > 0 ? forced : best);
+            return best;
+        };
+        uint32_t const nEdge = 1u + A.nEdgeRight, nInner = A.nWin - nEdge;
+        // Split: the interior windows' interior rows go to the bare-only kernel (128 registers, 4 CTAs per SM), this kernel
+        // keeps the edge windows, the strips and the S-row bands next to a physical ring. Needs rows for both bands.
+        // Measured (profiles/r02/heat_walk_probe_split.log, 16384^2, 960 steps): 4 levels 215 us per step split (225 without the
+        // dependent-launch overlap) against 196 in one kernel, 6 levels 185 against 183 -- a fourth CTA per SM does not pay
+        // for the second launch and the shallower stage ring, so the split stays OFF by default.
+        bool const split = SPLIT_OK && nInner > 0 && b200::tune("heat.walk_split", 0) != 0
+                           && int64_t(A.hiY) - A.loY + 1 >= int64_t(4 * S) + 2 * A.sendRows;
+        // output rows: the core rows, plus the ring row on a physical side
+        int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
+        A.nFront = 0;
+        A.frontIsStrip = 0;
+        uint32_t nStrip = 0;
+        if(A.ghostTop)
+        {
+            // strip: the rows sent to the upper neighbour
+            A.frontY0[A.nFront] = A.loY;
+            A.frontY1[A.nFront] = A.loY + A.sendRows;
+            A.frontIsStrip |= 1u << A.nFront;
+            outLo = A.loY + A.sendRows;
+            ++A.nFront;
+            ++nStrip;
+        }
+        else if(split)
+        {
+            // band: the ring row and the S - 1 core rows whose lower levels touch it
+            A.frontY0[A.nFront] = outLo;
+            A.frontY1[A.nFront] = A.loY + S - 1;
+            outLo = A.loY + S - 1;
+            ++A.nFront;
+        }
+        if(A.ghostBottom)
+        {
+            A.frontY0[A.nFront] = A.hiY + 1 - A.sendRows;
+            A.frontY1[A.nFront] = A.hiY + 1;
+            A.frontIsStrip |= 1u << A.nFront;
+            outHi = A.hiY - A.sendRows;
+            ++A.nFront;
+            ++nStrip;
+        }
+        else if(split)
+        {
+            A.frontY0[A.nFront] = A.hiY - S + 2;
+            A.frontY1[A.nFront] = outHi + 1;
+            outHi = A.hiY - S + 1;
+            ++A.nFront;
+        }
+        A.intY0 = outLo;
+        A.intY1 = outHi + 1;
+        int64_t const rowsInt = int64_t(A.intY1) - A.intY0;
+        int64_t const forced = b200::tune("heat.walk_seg_rows", 0);
+        uint32_t nSeg = 0;
+        A.segRows = 1;
+        if(rowsInt > 0)
+        {
+            // in split mode this kernel walks the interior rows with the edge windows only: short segments, so that it is over
+            // long before the bare-only kernel that runs next to it
+            A.segRows = int32_t(forced > 0 ? forced : (split ? std::min<int64_t>(rowsInt, 128) : pickSegRows(rowsInt, A.nWin, slots, 0.3)));
             nSeg = uint32_t((rowsInt + A.segRows - 1) / A.segRows);
         }
-        A.nSegAll = A.nStrip + nSeg;
-        uint64_t const walkers = uint64_t(A.nSegAll) * A.nWin;
+        A.nSegAll = A.nFront + nSeg;
+        uint64_t const walkers = split ? uint64_t(nEdge) * A.nSegAll + uint64_t(nInner) * A.nFront : uint64_t(A.nSegAll) * A.nWin;
         B200_REQUIRE(walkers <= 0x7fffffffull, B200_ERANGE);
         A.nWalkers = uint32_t(walkers);
-        A.stripTiles = A.nStrip * A.nWin; // strip WALKERS: each counts itself once
-        unsigned const grid = unsigned((walkers + kWalkWarps - 1) / kWalkWarps);
-        kernel<<<grid, 32 * kWalkWarps, smemBytes, s>>>(plan->mapW[src_index], A);
-        B200_LAUNCH_CHECK();
+        A.stripTiles = nStrip * A.nWin; // strip WALKERS: each counts itself once
+        if(walkers > 0)
+        {
+            unsigned const grid = unsigned((walkers + kWalkWarps - 1) / kWalkWarps);
+            kernel<<<grid, 32 * kWalkWarps, smemBytes, s>>>(plan->mapW[src_index], A);
+            B200_LAUNCH_CHECK();
+        }
+        if constexpr(SPLIT_OK)
+        {
+            if(split && rowsInt > 0)
+            {
+                // the bare-only kernel: 3 stages of R rows (48 KB per CTA at R = 4: four CTAs per SM), its own segmentation
+                constexpr int STB = 3;
+                constexpr size_t smemBare = size_t(kWalkWarps) * STB * R * BOXX * 8;
+                constexpr int MINBB = S == 4 ? 4 : 3; // 128 / 168 registers
+                auto* const bSq = heatWalkKernel<S, R, STB, true, MINBB, SWAP, true>;
+                auto* const bGen = heatWalkKernel<S, R, STB, false, MINBB, SWAP, true>;
+                auto* const bare = sq ? bSq : bGen;
+                static int bareSlotsPerSm[2][64] = {};
+                int bareSlots;
+                {
+                    std::lock_guard<std::mutex> lock(mtx);
+                    int& cached = bareSlotsPerSm[sq ? 1 : 0][plan->dev & 63];
+                    if(cached == 0)
+                    {
+                        B200_CUDA(cudaFuncSetAttribute(bare, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBare)));
+                        int ctas = 0;
+                        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, bare, 32 * kWalkWarps, smemBare));
+                        cached = (ctas > 0 ? ctas : 1) * kWalkWarps;
+                    }
+                    bareSlots = cached * b200::smCount(plan->dev);
+                }
+                HeatWArgs B = A;
+                B.segRows = int32_t(forced > 0 ? forced : pickSegRows(rowsInt, nInner, bareSlots, 0.1));
+                uint64_t const bareWalkers = uint64_t((rowsInt + B.segRows - 1) / B.segRows) * nInner;
+                B200_REQUIRE(bareWalkers <= 0x7fffffffull, B200_ERANGE);
+                B.nWalkers = uint32_t(bareWalkers);
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(unsigned((bareWalkers + kWalkWarps - 1) / kWalkWarps));
+                cfg.blockDim = dim3(32 * kWalkWarps);
+                cfg.dynamicSmemBytes = smemBare;
+                cfg.stream = s;
+                cudaLaunchAttribute attr{};
+                attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr.val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = &attr;
+                cfg.numAttrs = (walkers > 0 && b200::tune("heat.walk_pdl", 1) != 0) ? 1 : 0;
+                B200_CUDA(cudaLaunchKernelEx(&cfg, bare, plan->mapW[src_index], B));
+                b200::countLaunch();
+            }
+        }
         return 0;
     }
 
@@ -1620,23 +1726,32 @@ namespace
         {
             // the default shape also exists with conflict-free loads (heat.walk_lds_swap)
             bool const swap = R_ == 4 && ST_ == 4 && b200::tune("heat.walk_lds_swap", 0) != 0;
+            // (the default shape R4 x ST4 at the default register budget can split the interior off: SPLIT_OK, 4 and 6 levels)
             if constexpr(S_ == 4)
             {
                 if(minb >= 4)
                     return launchWalkShape<S_, R_, ST_, 4>(plan, s, src_index, A, sq);
                 if constexpr(R_ == 4 && ST_ == 4)
+                {
                     if(swap)
                         return launchWalkShape<S_, R_, ST_, 3, true>(plan, s, src_index, A, sq);
-                return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
+                    return launchWalkShape<S_, R_, ST_, 3, false, true>(plan, s, src_index, A, sq);
+                }
+                else
+                    return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
             }
             else
             {
                 if(minb >= 3)
                     return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
                 if constexpr(R_ == 4 && ST_ == 4)
+                {
                     if(swap)
                         return launchWalkShape<S_, R_, ST_, 2, true>(plan, s, src_index, A, sq);
-                return launchWalkShape<S_, R_, ST_, 2>(plan, s, src_index, A, sq);
+                    return launchWalkShape<S_, R_, ST_, 2, false, S_ == 6>(plan, s, src_index, A, sq);
+                }
+                else
+                    return launchWalkShape<S_, R_, ST_, 2>(plan, s, src_index, A, sq);
             }
         };
         switch(levels * 100 + shape)

@@ -89,15 +89,18 @@ def test_heat2d_n_level_kernel_every_tile_shape(gpu, cfg):
     assert got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("split", [0, 1], ids=["one_kernel", "interior_in_bare_kernel"])
 @pytest.mark.parametrize("seg_rows", [0, 40, 7], ids=lambda r: f"seg{r}")
-@pytest.mark.parametrize("shape_key", [43, 44, 46, 26], ids=lambda k: f"R{k // 10}_stages{k % 10}")
+@pytest.mark.parametrize("shape_key", [0, 43, 44, 46, 26], ids=lambda k: f"R{k // 10}_stages{k % 10}")
 @pytest.mark.parametrize("levels", [4, 6, 8])
 @pytest.mark.parametrize("square", [False, True], ids=["rx_ne_ry", "square_cells"])
-def test_heat2d_walker_kernel_every_shape(gpu, square, levels, shape_key, seg_rows):
+def test_heat2d_walker_kernel_every_shape(gpu, square, levels, shape_key, seg_rows, split):
     """Every instantiation of the walker kernel (heatWalkKernel: one warp walks down a 128-column window, levels kept as
     partial sums in registers) on a rough field: partial windows on the right edge, several row segments per window
     (heat.walk_seg_rows forces short ones, down to segments shorter than the 2S-row prologue), chunk counts that do not
-    divide the stage ring, both product forms (square cells share v*rX). Bit-exact against the oracle, ring included."""
+    divide the stage ring, both product forms (square cells share v*rX), and with the interior windows' interior rows split
+    off into the bare-only kernel launched next to the full one (heat.walk_split = 1, the default shape at 4 and 6 levels).
+    Bit-exact against the oracle, ring included."""
     ab, dev, queue = gpu
     ny, nx = (333, 333) if square else (203, 391)
     dx, dy, dt = ol.heat_params(ny, nx)
@@ -107,11 +110,13 @@ def test_heat2d_walker_kernel_every_shape(gpu, square, levels, shape_key, seg_ro
     want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
     ab.runtime.tune_set("heat.walk_shape", shape_key)
     ab.runtime.tune_set("heat.walk_seg_rows", seg_rows)
+    ab.runtime.tune_set("heat.walk_split", split)
     try:
         got = _run_gpu(ab, queue, u0, steps, dx, dy, dt, fuse=levels)
     finally:
         ab.runtime.tune_set("heat.walk_shape", 0)
         ab.runtime.tune_set("heat.walk_seg_rows", 0)
+        ab.runtime.tune_set("heat.walk_split", 0)
     assert got.tobytes() == want.tobytes()
 
 

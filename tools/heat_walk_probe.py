@@ -26,19 +26,18 @@ def t(fn, n):
 
 
 long_steps = int(os.environ.get("LONG_STEPS", "960"))  # a multiple of 2, 3, 4, 6, 8
-RESET = {"heat.walk": 1, "heat.walk_shape": 0, "heat.walk_seg_rows": 0, "heat.walk_minb": 0, "heat.walk_lds_swap": 0}
+RESET = {"heat.walk": 1, "heat.walk_shape": 0, "heat.walk_seg_rows": 0, "heat.walk_minb": 0, "heat.walk_lds_swap": 0, "heat.walk_split": 0,
+         "heat.walk_pdl": 1}
 cases = [("tile  4", 4, {"heat.walk": 0})]
-for S in (4, 6, 8):
-    cases.append((f"walk  {S} default", S, {}))
-for S in (4, 6, 8):
-    for shape in (43, 44, 46):
-        cases.append((f"walk  {S} R{shape // 10}x{shape % 10}", S, {"heat.walk_shape": shape}))
-cases.append(("walk  6 minb3", 6, {"heat.walk_minb": 3}))
-for S in (4, 6, 8, 4, 8):
-    cases.append((f"walk  {S} lds_swap", S, {"heat.walk_lds_swap": 1}))
-    cases.append((f"walk  {S} plain", S, {}))
+for rep in range(2):
+    for S in (4, 6, 8):
+        cases.append((f"walk  {S} default (one kernel)", S, {}))
+        if S != 8:
+            cases.append((f"walk  {S} split", S, {"heat.walk_split": 1}))
+            cases.append((f"walk  {S} split, no pdl", S, {"heat.walk_split": 1, "heat.walk_pdl": 0}))
+        cases.append((f"walk  {S} lds_swap", S, {"heat.walk_lds_swap": 1}))
 for seg in (64, 128, 256, 512):
-    for S in (4, 8):
+    for S in (4, 6):
         cases.append((f"walk  {S} seg{seg}", S, {"heat.walk_seg_rows": seg}))
 for name, S, tune in cases:
     for k, v in tune.items():
