@@ -241,8 +241,8 @@ def test_reduce_f32_exactly_representable_sums(tmp_path):
 
 
 # ---------------------------------------------------------------------------------- heatEquation2D
-@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("fused2", True, True), ("fused3", True, True), ("fused4", True, True), ("functors", True, True),
-                                               ("functors", False, False)])
+@pytest.mark.parametrize("mode,native,exact", [("fused", True, True), ("fused2", True, True), ("fused3", True, True), ("fused4", True, True), ("fused6", True, True), ("fused8", True, True),
+                                               ("functors", True, True), ("functors", False, False)])
 @pytest.mark.parametrize("shape", [(64, 64), (96, 160)])
 def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
     """fused (one and two steps per launch) and recognised-functor paths: bit-exact (boundary factors from the host
@@ -265,7 +265,7 @@ def test_heat2d_cpp_driver_vs_oracle(tmp_path, mode, native, exact, shape):
         assert float(np.max(np.abs(got - want))) <= 1e-12
 
 
-@pytest.mark.parametrize("levels", [2, 3, 4])
+@pytest.mark.parametrize("levels", [2, 3, 4, 6, 8])
 @pytest.mark.parametrize("slabs,shape", [(3, (96, 160)), (2, (256, 700)), (1, (64, 64))])
 def test_heat2d_cpp_slabs_vs_oracle(tmp_path, slabs, shape, levels):
     """alpaka::b200::Heat2DSlabs: K row slabs in one process (here all on device 0), `levels` time levels per launch and per
