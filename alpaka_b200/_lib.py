@@ -177,6 +177,8 @@ SIGNATURES: dict[str, list] = {
     "b200_heat2d_stepn_f64": [_vp, _vp, _i, _f64, _f64, _i, _vp],
     "b200_heat2d_slab_plan_create": [_i, _vp, _vp, _sz, _u32, _u32, _vp, _vp, _i, _u32, _P(_vp)],
     "b200_heat2d_stepn_halo_f64": [_vp, _vp, _i, _f64, _f64, _i, _vp, _u32],
+    "b200_heat2d_tile_plan_create": [_i, _vp, _vp, _sz, _u32, _u32, _vp, _vp, _i, _u32, _P(_vp)],
+    "b200_heat2d_stepn_tile_f64": [_vp, _vp, _i, _f64, _f64, _i, _vp, _u32],
     "b200_heat2d_step2_halo_f64": [_vp, _vp, _i, _f64, _f64, _f64, _f64, _u32],
     "b200_heat2d_step_window_f64": [_vp, _vp, _i, _f64, _f64, _f64, _u32, _u32, _u32, _u32],
     "b200_heat2d_boundary_f64": [_vp, _vp, _i, _f64],

@@ -997,9 +997,28 @@ namespace
         int32_t intY0, intY1, segRows; // interior output rows [intY0, intY1) in segments of segRows
         uint32_t nWalkers;
         int32_t rows; // rows of the array (sy has that many entries)
+        // columns of the array: [0, nx + 2 padX). padX = 1: the reference layout / row slabs (ring columns 0 and nx+1).
+        // padX = G: a 2-D tile whose ghost columns are G deep (b200_heat2d_tile_plan_create), as the rows of a slab
+        int32_t loX, hiX; // first / last core column = padX, nx + padX - 1
+        int32_t ghostLeft, ghostRight; // 1: that side has a neighbour
+        uint32_t const* colFlags[2]; // my flag words set by the left / right neighbour's column exchange, or null
         int32_t align32; // 1: rows of dst (and of the peers' arrays) are 32-byte aligned -> 256-bit stores
         double sxLeft, sxRight; // sx[0], sx[nx+1]: the ring columns' factors
     };
+
+    // ringOrZeroN with the columns generalised: a cell of a level the stencil does not produce -- exactSolution where it is a
+    // boundary cell (physical ring rows over the columns [iLo, iHi] on which the level is defined, physical ring columns
+    // over the rows [jLo, jHi]), 0 anywhere else (never consumed).
+    __device__ __forceinline__ double ringOrZeroW(HeatWArgs const& A, int32_t j, int32_t i, int32_t jLo, int32_t jHi, int32_t iLo, int32_t iHi, double tf)
+    {
+        bool const iDefined = i >= iLo && i <= iHi;
+        bool const jDefined = j >= jLo && j <= jHi;
+        bool const rowRing = (j == A.loY - 1 && !A.ghostTop) || (j == A.hiY + 1 && !A.ghostBottom);
+        bool const colRing = (i == A.loX - 1 && !A.ghostLeft) || (i == A.hiX + 1 && !A.ghostRight);
+        if((rowRing && iDefined) || (colRing && jDefined))
+            return __dmul_rn(tf, __dadd_rn(__ldg(A.sx + i), __ldg(A.sy + j)));
+        return 0.0;
+    }
 
     constexpr int kWalkCols = 4; // columns per lane
 
@@ -1087,7 +1106,7 @@ namespace
 #pragma unroll
                     for(int i = 0; i < kWalkCols; ++i)
                         if(ringMask & (1u << i))
-                            v[i] = __dmul_rn(A.tf[l], __dadd_rn(gi + i == 0 ? A.sxLeft : A.sxRight, syw[l]));
+                            v[i] = __dmul_rn(A.tf[l], __dadd_rn(gi + i < A.loX ? A.sxLeft : A.sxRight, syw[l]));
                 }
             }
             if(l + 1 < S)
@@ -1097,11 +1116,12 @@ namespace
                     // rows on which level l+1 is defined: the core rows, and on a side with a neighbour the S-(l+1) rows
                     // beyond them that deeper levels still need
                     int32_t const jLo = A.loY - (S - (l + 1)) * A.ghostTop, jHi = A.hiY + (S - (l + 1)) * A.ghostBottom;
+                    int32_t const iLo = A.loX - (S - (l + 1)) * A.ghostLeft, iHi = A.hiX + (S - (l + 1)) * A.ghostRight;
                     bool const jDefined = gj >= jLo && gj <= jHi;
 #pragma unroll
                     for(int i = 0; i < kWalkCols; ++i)
-                        if(!(jDefined && gi + i >= 1 && gi + i <= int32_t(A.nx)))
-                            v[i] = ringOrZeroN(A, gj, gi + i, jLo, jHi, A.tf[l]);
+                        if(!(jDefined && gi + i >= iLo && gi + i <= iHi))
+                            v[i] = ringOrZeroW(A, gj, gi + i, jLo, jHi, iLo, iHi, A.tf[l]);
                 }
             }
             else if(storeLane && gj >= ya && gj < yb)
@@ -1129,11 +1149,12 @@ namespace
                     for(int i = 0; i < kWalkCols; ++i)
                     {
                         int32_t const c = gi + i;
-                        if((jCore || jRing) && c >= 0 && c <= int32_t(A.nx) + 1)
+                        bool const iCore = c >= A.loX && c <= A.hiX;
+                        bool const iRing = (c == A.loX - 1 && !A.ghostLeft) || (c == A.hiX + 1 && !A.ghostRight);
+                        if((jCore || jRing) && (iCore || iRing))
                         {
-                            bool const iCore = c >= 1 && c <= int32_t(A.nx);
                             if(!(jCore && iCore))
-                                v[i] = ringOrZeroN(A, gj, c, A.loY, A.hiY, A.tf[S - 1]);
+                                v[i] = ringOrZeroW(A, gj, c, A.loY, A.hiY, A.loX, A.hiX, A.tf[S - 1]);
                             if(jCore || iCore)
                                 wr |= 1u << i;
                         }
@@ -1246,9 +1267,29 @@ namespace
             for(int s = 0; s < ST; ++s)
                 mbarInit(&bar[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            // strip walkers read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
-            if(strip && A.myFlags != nullptr)
-                waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
+            if constexpr(!BAREONLY)
+            {
+                // strip walkers read ghost rows and overwrite the neighbours' ghost rows: wait for the neighbours' previous launch
+                if(strip && A.myFlags != nullptr)
+                    waitForNeighbours(A.peerDst, A.myFlags, A.step, A.status, A.waitNs);
+                // 2-D tiles: walkers whose window or rows touch ghost COLUMNS (every window that is not bare, and the strips,
+                // whose corners come with them) wait for the column exchange that followed the neighbours' previous launch
+                bool const bareWin = cx >= A.loX - (A.ghostLeft ? A.loX : 0) && cx + BOXX - 1 <= A.hiX + (A.ghostRight ? A.loX : 0)
+                                     && cx >= A.loX && cx + BOXX - 1 <= A.hiX;
+                if(strip || !bareWin)
+                {
+                    bool waited = false;
+                    for(int side = 0; side < 2; ++side)
+                        if(A.colFlags[side] != nullptr)
+                        {
+                            if(!b200::waitFlagAtLeast(A.colFlags[side], A.step, 1u, A.waitNs))
+                                atomicExch(A.status, 3u + uint32_t(side));
+                            waited = true;
+                        }
+                    if(waited)
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                }
+            }
 #pragma unroll
             for(int s = 0; s < ST; ++s)
                 if(s < nChunks)
@@ -1260,16 +1301,19 @@ namespace
         __syncwarp();
 
         bool const storeLane = lane >= G::LOST && lane < 32 - G::LOST;
-        // every column of the window is a core column
-        bool const colInterior = cx >= 1 && cx + BOXX - 1 <= int32_t(A.nx);
-        uint32_t ringMask = 0u, validMask = 0u;
+        // bare window: every column holds field data with no ring column among them (core columns, or a neighbour's ghost
+        // columns), and every STORED column is a core column
+        bool const colInterior = cx >= A.loX - (A.ghostLeft ? A.loX : 0) && cx + BOXX - 1 <= A.hiX + (A.ghostRight ? A.loX : 0)
+                                 && cx + kWalkCols * G::LOST >= A.loX && cx + BOXX - 1 - kWalkCols * G::LOST <= A.hiX;
+        uint32_t ringMask = 0u, validMask = 0u; // bit i: column gi + i is a physical ring column / a column this rank owns
 #pragma unroll
         for(int i = 0; i < kWalkCols; ++i)
         {
             int32_t const c = gi + i;
-            if(c == 0 || c == int32_t(A.nx) + 1)
+            bool const ring = (c == A.loX - 1 && !A.ghostLeft) || (c == A.hiX + 1 && !A.ghostRight);
+            if(ring)
                 ringMask |= 1u << i;
-            if(c >= 0 && c <= int32_t(A.nx) + 1)
+            if(ring || (c >= A.loX && c <= A.hiX))
                 validMask |= 1u << i;
         }
         WalkState<S> st;
@@ -1392,6 +1436,69 @@ namespace
         }
     }
 
+    // ---- the COLUMN exchange of a 2-D tile with ghost cells G deep (second phase of the halo exchange; the rows travel inside
+    // the walker launch). After launch L every rank stores its first / last G core columns -- over ALL rows that hold level
+    // data, the ghost rows just received from the vertical neighbours included, which is how the corner blocks reach the
+    // diagonal neighbours without a third partner -- into the left / right neighbour's ghost columns and publishes L in their
+    // column flag words. Block 0..n-1 share the rows; the first thread of every block waits for the vertical neighbours'
+    // row flags of THIS launch before anything is read.
+    struct HaloColsArgs
+    {
+        double const* src; // the buffer launch L wrote
+        size_t pitchElems;
+        int32_t rowLo, rowHi; // inclusive row range that holds level data
+        int32_t loX, hiX, G;
+        double* peer[2]; // [left, right] neighbour's same buffer, or null
+        uint32_t* peerFlag[2]; // their flag word for my side
+        uint32_t const* rowFlags[2]; // my flag words set by the top / bottom neighbour's launch, or null
+        uint32_t* counter; // blocks finished (reset by the last one)
+        uint32_t* status;
+        uint64_t waitNs;
+        uint32_t step;
+    };
+
+    __global__ void __launch_bounds__(256) haloColsKernel(HaloColsArgs const A)
+    {
+        if(threadIdx.x == 0)
+        {
+            for(int side = 0; side < 2; ++side)
+                if(A.rowFlags[side] != nullptr && !b200::waitFlagAtLeast(A.rowFlags[side], A.step, 0u, A.waitNs))
+                    atomicExch(A.status, 1u + uint32_t(side));
+        }
+        __syncthreads();
+        int64_t const nRows = int64_t(A.rowHi) - A.rowLo + 1;
+        int64_t const perSide = nRows * A.G;
+        for(int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < 2 * perSide; t += int64_t(gridDim.x) * blockDim.x)
+        {
+            int const side = t >= perSide ? 1 : 0;
+            if(A.peer[side] == nullptr)
+                continue;
+            int64_t const u = t - side * perSide;
+            int64_t const row = A.rowLo + u / A.G;
+            int32_t const c = int32_t(u % A.G);
+            // my first G core columns are the left neighbour's right ghost columns, my last G its left ones
+            int32_t const from = side == 0 ? A.loX + c : A.hiX - A.G + 1 + c;
+            int32_t const to = side == 0 ? A.hiX + 1 + c : A.loX - A.G + c;
+            // (ld.volatile: the ghost rows were written by peers during this launch; the flag wait above ordered them)
+            double const v = *reinterpret_cast<double const volatile*>(A.src + row * int64_t(A.pitchElems) + from);
+            A.peer[side][row * int64_t(A.pitchElems) + to] = v;
+        }
+        __syncthreads();
+        if(threadIdx.x == 0)
+        {
+            __threadfence_system();
+            uint32_t const done = atomicAdd(A.counter, 1u);
+            if(done == gridDim.x - 1u)
+            {
+                __threadfence_system();
+                *A.counter = 0u;
+                for(int side = 0; side < 2; ++side)
+                    if(A.peerFlag[side] != nullptr)
+                        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
+            }
+        }
+    }
+
     // Ring only (BoundaryKernel.hpp:63-84): top/bottom rows i = 1..nx, left/right columns j = 1..ny, corners untouched.
     // One thread per ring cell: [0,nx) top, [nx,2nx) bottom, [2nx,2nx+ny) left, [2nx+ny, 2nx+2ny) right.
     __global__ void __launch_bounds__(256) heatBoundaryKernel(HeatArgs const A)
@@ -1510,7 +1617,8 @@ struct b200_heat2d_plan_st
     CUtensorMap mapW[2]; // walker kernel: box 128 columns x R rows, keyed by mapWKey = R (0 = not built yet)
     int mapWKey = 0;
     double sxLeft = 0.0, sxRight = 0.0; // sx[0], sx[nx+1] (host copies for the walker's edge windows)
-    uint32_t padY = 1; // 1: reference layout (ny+2 rows); 2: row slab with ghost rows two deep (ny+4 rows)
+    uint32_t padY = 1; // 1: reference layout (ny+2 rows); G: row slab / tile with ghost rows G deep (ny+2G rows)
+    uint32_t padX = 1; // 1: the reference's one-cell ring in the columns; G: 2-D tile with ghost columns G deep (nx+2G columns)
     // fused halo exchange (b200_heat2d_plan_set_halo)
     bool hasHalo = false;
     b200_heat2d_halo halo{};
@@ -1552,22 +1660,44 @@ namespace
             if(!enc)
                 return b200::fail(B200_ENODEV, "cuTensorMapEncodeTiled entry point", __FILE__, __LINE__);
             for(int b = 0; b < 2; ++b)
-                if(!encodeFieldMap(enc, &plan->mapW[b], plan->u[b], plan->pitchBytes, rows, plan->nx, R, BOXX))
+                if(!encodeFieldMap(enc, &plan->mapW[b], plan->u[b], plan->pitchBytes, rows, plan->nx + 2 * plan->padX - 2, R, BOXX))
                     return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled (walker box)", __FILE__, __LINE__);
             plan->mapWKey = R;
         }
         A.rows = int32_t(rows);
         A.sxLeft = plan->sxLeft;
         A.sxRight = plan->sxRight;
+        A.loX = int32_t(plan->padX);
+        A.hiX = int32_t(plan->nx + plan->padX - 1);
+        A.ghostLeft = (plan->edges & B200_EDGE_LEFT) ? 0 : 1;
+        A.ghostRight = (plan->edges & B200_EDGE_RIGHT) ? 0 : 1;
+        A.colFlags[0] = A.colFlags[1] = nullptr;
+        if(A.myFlags != nullptr && plan->padX > 1)
+        {
+            // 2-D tile: the ghost columns arrive by the column exchange that follows every launch (haloColsKernel)
+            if(A.ghostLeft)
+                A.colFlags[0] = plan->halo.my_flags + 2;
+            if(A.ghostRight)
+                A.colFlags[1] = plan->halo.my_flags + 3;
+        }
         auto aligned32 = [](void const* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 32 == 0; };
         A.align32 = plan->pitchBytes % 32 == 0 && aligned32(A.dst) && aligned32(A.peerDst[0]) && aligned32(A.peerDst[1]) ? 1 : 0;
-        A.nWin = (plan->nx + 2 + uint32_t(WW) - 1) / uint32_t(WW);
-        // edge windows: window 0 (its first lanes lie left of the field) and the windows at the right end whose 128 columns
-        // reach beyond column nx; at least one window is counted on the left, the rest of the edge windows on the right
+        // windows cover the columns 0 .. hiX + 1 (window w stores columns [w WW, (w+1) WW))
+        A.nWin = (uint32_t(A.hiX) + 2 + uint32_t(WW) - 1) / uint32_t(WW);
+        // bare windows (the kernel's colInterior): field data in all 128 columns, no ring column among them, core columns
+        // stored. The others -- window 0 and the last few -- are the edge windows, dispatched first.
+        auto const isBare = [&](uint32_t w)
+        {
+            int64_t const cx = int64_t(w) * WW - kWalkCols * WalkGeom<S>::LOST;
+            return cx >= A.loX - (A.ghostLeft ? A.loX : 0) && cx + BOXX - 1 <= A.hiX + (A.ghostRight ? A.loX : 0)
+                   && cx + kWalkCols * WalkGeom<S>::LOST >= A.loX && cx + BOXX - 1 - kWalkCols * WalkGeom<S>::LOST <= A.hiX;
+        };
         A.nEdgeRight = 0;
-        while(A.nEdgeRight + 1 < A.nWin
-              && int64_t(A.nWin - 1 - A.nEdgeRight) * WW - kWalkCols * WalkGeom<S>::LOST + BOXX - 1 > int64_t(plan->nx))
+        while(A.nEdgeRight + 1 < A.nWin && !isBare(A.nWin - 1 - A.nEdgeRight))
             ++A.nEdgeRight;
+        bool middleAllBare = true; // (window 0 is never bare: its first lanes lie left of column 0)
+        for(uint32_t w = 1; w + A.nEdgeRight < A.nWin; ++w)
+            middleAllBare = middleAllBare && isBare(w);
         // Segments per window for `rowsInt` rows on `slots` resident walkers: maximise (share of the slots used over all
         // waves) x (share of a walker's rows that are not its 2S-row prologue) x waves / (waves + tail) -- the last factor
         // models the tail a slower walker of the last wave leaves; it favours a few waves over exactly one.
@@ -1597,7 +1727,7 @@ namespace
         // Measured (profiles/r02/heat_walk_probe_split.log, 16384^2, 960 steps): 4 levels 215 us per step split (225 without the
         // dependent-launch overlap) against 196 in one kernel, 6 levels 185 against 183 -- a fourth CTA per SM does not pay
         // for the second launch and the shallower stage ring, so the split stays OFF by default.
-        bool const split = SPLIT_OK && nInner > 0 && b200::tune("heat.walk_split", 0) != 0
+        bool const split = SPLIT_OK && nInner > 0 && middleAllBare && b200::tune("heat.walk_split", 0) != 0
                            && int64_t(A.hiY) - A.loY + 1 >= int64_t(4 * S) + 2 * A.sendRows;
         // output rows: the core rows, plus the ring row on a physical side
         int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
@@ -1801,11 +1931,12 @@ extern "C"
             double const* sy_host,
             int edges,
             uint32_t padY,
-            b200_heat2d_plan_t* out)
+            b200_heat2d_plan_t* out,
+            uint32_t padX = 1)
         {
             B200_REQUIRE(out && u0 && u1 && sx_host && sy_host, B200_EINVAL);
             B200_REQUIRE(ny >= 1 && nx >= 1 && (edges & ~B200_EDGE_ALL) == 0, B200_EINVAL);
-            B200_REQUIRE(pitch_bytes >= (size_t(nx) + 2) * 8, B200_EINVAL);
+            B200_REQUIRE(pitch_bytes >= (size_t(nx) + 2 * padX) * 8, B200_EINVAL);
             B200_REQUIRE(pitch_bytes % 16 == 0, B200_EALIGN);
             B200_REQUIRE(reinterpret_cast<uintptr_t>(u0) % 16 == 0 && reinterpret_cast<uintptr_t>(u1) % 16 == 0, B200_EALIGN);
             B200_REQUIRE(uint64_t(ny) + 4 + 64 < 0x7fffffffull && uint64_t(nx) + 2 + TX < 0x7fffffffull, B200_ERANGE);
@@ -1823,18 +1954,19 @@ extern "C"
             plan->nx = nx;
             plan->edges = edges;
             plan->padY = padY;
-            plan->sxLeft = sx_host[0];
-            plan->sxRight = sx_host[size_t(nx) + 1];
+            plan->padX = padX;
+            plan->sxLeft = sx_host[padX - 1];
+            plan->sxRight = sx_host[size_t(nx) + padX];
             uint64_t const rows = uint64_t(ny) + 2 * padY;
             for(int b = 0; b < 2; ++b)
             {
-                if(!encodeFieldMap(enc, &plan->map[b], plan->u[b], pitch_bytes, rows, nx, BOX_Y))
+                if(!encodeFieldMap(enc, &plan->map[b], plan->u[b], pitch_bytes, rows, nx + 2 * padX - 2, BOX_Y))
                 {
                     delete plan;
                     return b200::fail(B200_EINVAL, "cuTensorMapEncodeTiled", __FILE__, __LINE__);
                 }
             }
-            size_t const bx = (size_t(nx) + 2) * 8, by = size_t(rows) * 8;
+            size_t const bx = (size_t(nx) + 2 * padX) * 8, by = size_t(rows) * 8;
             cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&plan->sx), bx);
             if(e == cudaSuccess)
                 e = cudaMalloc(reinterpret_cast<void**>(&plan->sy), by);
@@ -2029,7 +2161,7 @@ extern "C"
         uint32_t i0,
         uint32_t i1)
     {
-        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && plan->padY == 1, B200_EINVAL);
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && plan->padY == 1 && plan->padX == 1, B200_EINVAL);
         B200_REQUIRE(j1 <= plan->ny + 2 && i1 <= plan->nx + 2, B200_EINVAL);
         B200_CUDA(cudaSetDevice(plan->dev));
         HeatArgs A = baseArgs(plan, src_index, rx, ry, time_factor);
@@ -2039,7 +2171,7 @@ extern "C"
 
     int b200_heat2d_boundary_f64(b200_heat2d_plan_t plan, b200_stream_t stream, int dst_index, double time_factor)
     {
-        B200_REQUIRE(plan && (dst_index == 0 || dst_index == 1) && plan->padY == 1, B200_EINVAL);
+        B200_REQUIRE(plan && (dst_index == 0 || dst_index == 1) && plan->padY == 1 && plan->padX == 1, B200_EINVAL);
         B200_CUDA(cudaSetDevice(plan->dev));
         HeatArgs A{};
         A.dst = plan->u[dst_index];
@@ -2181,7 +2313,8 @@ extern "C"
         {
             B200_CUDA(cudaSetDevice(plan->dev));
             // even depths from 4 on: the walker kernel (heat.walk = 0 keeps the round-1 tile kernel for 4 levels)
-            bool const walk = levels >= 4 && levels % 2 == 0 && (levels > 4 || b200::tune("heat.walk", 1) != 0);
+            bool const walk = levels >= 4 && levels % 2 == 0 && (levels > 4 || plan->padX > 1 || b200::tune("heat.walk", 1) != 0);
+            B200_REQUIRE(walk || plan->padX == 1, B200_EINVAL); // ghost columns: the walker kernel only
             int const rpt = int(b200::tune("heat.stepn_rpt", 16));
             int const nwy = int(b200::tune("heat.stepn_nwy", 2));
             int const tyt = rpt * nwy;
@@ -2320,7 +2453,7 @@ extern "C"
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors && step >= 1, B200_EINVAL);
         B200_REQUIRE(levels == 3 || levels == 4 || levels == 6 || levels == 8, B200_EINVAL);
         // the ghost rows must be at least as deep as the launch advances (all of them are refreshed by every launch)
-        B200_REQUIRE(plan->hasHalo && plan->padY >= uint32_t(levels), B200_EINVAL);
+        B200_REQUIRE(plan->hasHalo && plan->padY >= uint32_t(levels) && plan->padX == 1, B200_EINVAL);
         return launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, step);
     }
 
@@ -2336,8 +2469,76 @@ extern "C"
     {
         B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && step >= 1, B200_EINVAL);
         // the ghost rows must be at least as deep as the launch advances (all of them are refreshed by every launch)
-        B200_REQUIRE(plan->hasHalo && plan->padY >= 2, B200_EINVAL);
+        B200_REQUIRE(plan->hasHalo && plan->padY >= 2 && plan->padX == 1, B200_EINVAL);
         return launchStep2(plan, stream, src_index, rx, ry, time_factor_1, time_factor_2, step);
+    }
+
+    int b200_heat2d_tile_plan_create(
+        int dev,
+        double* u0,
+        double* u1,
+        size_t pitch_bytes,
+        uint32_t ny,
+        uint32_t nx,
+        double const* sx_host,
+        double const* sy_host,
+        int edges,
+        uint32_t ghost,
+        b200_heat2d_plan_t* out)
+    {
+        // ghost cells `ghost` deep on every side; the border rows / columns sent to the neighbours must be distinct
+        B200_REQUIRE(ghost >= 4 && ghost <= uint32_t(kMaxLevels) && ny >= 2 * ghost && nx >= 2 * ghost, B200_EINVAL);
+        return createPlan(dev, u0, u1, pitch_bytes, ny, nx, sx_host, sy_host, edges, ghost, out, ghost);
+    }
+
+    int b200_heat2d_stepn_tile_f64(
+        b200_heat2d_plan_t plan,
+        b200_stream_t stream,
+        int src_index,
+        double rx,
+        double ry,
+        int levels,
+        double const* time_factors,
+        uint32_t step)
+    {
+        B200_REQUIRE(plan && (src_index == 0 || src_index == 1) && time_factors && step >= 1, B200_EINVAL);
+        B200_REQUIRE(levels == 4 || levels == 6 || levels == 8, B200_EINVAL);
+        B200_REQUIRE(plan->hasHalo && plan->padX > 1 && plan->padX == plan->padY && plan->padY >= uint32_t(levels), B200_EINVAL);
+        // phase 1: the walker launch (rows travel to the vertical neighbours from its strips)
+        if(int const rc = launchStepN(plan, stream, src_index, rx, ry, levels, time_factors, step))
+            return rc;
+        // phase 2: the columns, ghost rows included
+        bool const left = !(plan->edges & B200_EDGE_LEFT), right = !(plan->edges & B200_EDGE_RIGHT);
+        if(!left && !right)
+            return 0;
+        int const dstIndex = 1 - src_index;
+        bool const top = !(plan->edges & B200_EDGE_TOP), bottom = !(plan->edges & B200_EDGE_BOTTOM);
+        HaloColsArgs H{};
+        H.src = plan->u[dstIndex];
+        H.pitchElems = plan->pitchBytes / 8;
+        int32_t const G = int32_t(plan->padY);
+        H.G = G;
+        H.loX = G;
+        H.hiX = int32_t(plan->nx) + G - 1;
+        H.rowLo = top ? 0 : G - 1; // ghost rows above, or the ring row
+        H.rowHi = int32_t(plan->ny) + G + (bottom ? G - 1 : 0);
+        H.peer[0] = left ? plan->halo.peer_u[2][dstIndex] : nullptr;
+        H.peer[1] = right ? plan->halo.peer_u[3][dstIndex] : nullptr;
+        H.peerFlag[0] = left ? plan->halo.peer_flag[2] : nullptr;
+        H.peerFlag[1] = right ? plan->halo.peer_flag[3] : nullptr;
+        H.rowFlags[0] = top ? plan->halo.my_flags + 0 : nullptr;
+        H.rowFlags[1] = bottom ? plan->halo.my_flags + 1 : nullptr;
+        H.counter = plan->haloScratch + 2;
+        H.status = plan->haloScratch + 1;
+        H.waitNs = b200::waitLimitNs();
+        H.step = step;
+        if(b200::tune("heat.halo_debug", 0) & 2)
+            H.rowFlags[0] = H.rowFlags[1] = nullptr;
+        int64_t const cells = 2 * (int64_t(H.rowHi) - H.rowLo + 1) * G;
+        unsigned const grid = unsigned(std::min<int64_t>(64, (cells + 255) / 256));
+        haloColsKernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(H);
+        B200_LAUNCH_CHECK();
+        return 0;
     }
 
     int b200_heat2d_plan_set_halo(b200_heat2d_plan_t plan, b200_heat2d_halo const* halo)

@@ -177,6 +177,70 @@ def slab_for(rank: int, world: int, NY: int, NX: int, ghost: int) -> Slab:
     return Slab(rank, world, NY // world, NX, ghost, edges, nb)
 
 
+@dataclass(frozen=True)
+class DeepTile:
+    """One rank's tile of a Py x Px decomposition for launches that advance several time levels: ghost cells `ghost` deep
+    on all four sides. Local array (ny + 2*ghost) x (nx + 2*ghost); local [j][i] is global padded [gj0 + j][gi0 + i] (negative
+    or beyond the field on a physical side: those cells are unused). Core cells are [ghost, ny+ghost) x [ghost, nx+ghost); on
+    a physical side the row / column next to them is the ring."""
+
+    rank: int
+    py: int
+    px: int
+    cy: int
+    cx: int
+    ny: int
+    nx: int
+    ghost: int
+    edges: int
+    neighbours: dict = field(default_factory=dict)
+
+    @property
+    def shape(self) -> tuple[int, int]:
+        return self.ny + 2 * self.ghost, self.nx + 2 * self.ghost
+
+    @property
+    def gj0(self) -> int:
+        return self.cy * self.ny - (self.ghost - 1)
+
+    @property
+    def gi0(self) -> int:
+        return self.cx * self.nx - (self.ghost - 1)
+
+    def owned(self) -> tuple[int, int, int, int]:
+        """[j0, j1) x [i0, i1) of the local cells this tile OWNS: its core cells plus the physical ring on boundary sides."""
+        g = self.ghost
+        j0 = g - 1 if self.edges & EDGE_TOP else g
+        j1 = self.ny + g + 1 if self.edges & EDGE_BOTTOM else self.ny + g
+        i0 = g - 1 if self.edges & EDGE_LEFT else g
+        i1 = self.nx + g + 1 if self.edges & EDGE_RIGHT else self.nx + g
+        return j0, j1, i0, i1
+
+    def window(self, global_field):
+        """This tile's local array cut out of a global (NY+2) x (NX+2) padded field; cells outside the field are 0."""
+        import numpy as np
+
+        rows, cols = self.shape
+        NYp, NXp = global_field.shape
+        out = np.zeros((rows, cols))
+        jl, jh = max(self.gj0, 0), min(self.gj0 + rows, NYp)
+        il, ih = max(self.gi0, 0), min(self.gi0 + cols, NXp)
+        out[jl - self.gj0 : jh - self.gj0, il - self.gi0 : ih - self.gi0] = global_field[jl:jh, il:ih]
+        return out
+
+    def stitch(self, global_out, local_field) -> None:
+        j0, j1, i0, i1 = self.owned()
+        global_out[self.gj0 + j0 : self.gj0 + j1, self.gi0 + i0 : self.gi0 + i1] = local_field[j0:j1, i0:i1]
+
+
+def deep_tile_for(rank: int, world: int, NY: int, NX: int, ghost: int, grid: Optional[tuple[int, int]] = None) -> DeepTile:
+    """Geometry of rank's tile with ghost cells `ghost` deep (the Py x Px grid of tile_for)."""
+    t = tile_for(rank, world, NY, NX, grid)
+    if ghost < 1 or t.ny < 2 * ghost or t.nx < 2 * ghost:
+        raise ValueError(f"deep_tile_for: tiles of {t.ny} x {t.nx} core cells are smaller than 2 x {ghost} ghost cells")
+    return DeepTile(rank, t.py, t.px, t.cy, t.cx, t.ny, t.nx, ghost, t.edges, t.neighbours)
+
+
 #: time levels one launch can advance: 1 (one-step kernel), 2, 3, 4 (tile kernels), 4, 6, 8 (walker kernel)
 SUPPORTED_DEPTHS = (1, 2, 3, 4, 6, 8)
 

@@ -280,6 +280,120 @@ class HeatSlab(_HaloWiring):
         self.flags.free()
 
 
+class HeatTileDeep(_HaloWiring):
+    """One rank's tile of a Py x Px decomposition advanced `levels` (4, 6 or 8) time levels per launch: ghost cells
+    `levels` deep on all four sides (b200_heat2d_tile_plan_create + b200_heat2d_stepn_tile_f64, include/b200/b200.h). The
+    exchange has two phases per launch: the rows travel inside the walker launch (peer stores from its strips, as for
+    HeatSlab), then a small column kernel stores the first / last G core columns -- over all rows, the freshly received
+    ghost rows included, so the corner blocks reach the diagonal neighbours through the vertical ones -- into the left /
+    right neighbours and publishes the launch index in their column flags. Same wiring calls as HeatTile."""
+
+    def __init__(self, queue: Queue, rank: int, world: int, NY: int, NX: int, dt: Optional[float] = None, levels: int = 4,
+                 grid: Optional[tuple] = None):
+        import math
+
+        G = int(levels)
+        if G not in (4, 6, 8):
+            raise B200Error(-1, "deep heat tiles advance 4, 6 or 8 time levels per launch")
+        try:
+            self.tile = decomp.deep_tile_for(rank, world, NY, NX, G, grid)
+        except ValueError as e:
+            raise B200Error(-1, str(e)) from None
+        self.queue, self.dev = queue, queue.dev
+        self.NY, self.NX, self.levels = NY, NX, G
+        ny, nx = self.tile.ny, self.tile.nx
+        self.dx, self.dy = 1.0 / (NX + 1), 1.0 / (NY + 1)
+        self.dt = 0.2 * min(self.dx * self.dx, self.dy * self.dy) if dt is None else dt
+        if heat2d.stability_ratio(self.dx, self.dy, self.dt) > 1.0:
+            raise B200Error(-1, "Stability condition check failed")
+        self.rx, self.ry = self.dt / (self.dx * self.dx), self.dt / (self.dy * self.dy)
+        self.bufs = [Buf(self.dev, np.float64, (ny + 2 * G, nx + 2 * G), queue, ipc=True) for _ in range(2)]
+        self.cur, self.step_index, self.launch_index = 0, 0, 0
+        pi = math.pi
+        self.sx = np.array([math.sin(pi * ((self.tile.gi0 + i) * self.dx)) for i in range(nx + 2 * G)], dtype=np.float64)
+        self.sy = np.array([math.sin(pi * ((self.tile.gj0 + j) * self.dy)) for j in range(ny + 2 * G)], dtype=np.float64)
+        plan = C.c_void_p()
+        lib = _lib.load()
+        check(lib.b200_heat2d_tile_plan_create(self.dev.idx, self.bufs[0].ptr, self.bufs[1].ptr, self.bufs[0].pitch_bytes,
+                                               ny, nx, self.sx.ctypes.data, self.sy.ctypes.data, self.tile.edges, G,
+                                               C.byref(plan)))
+        self.plan = plan.value
+        self.flags = Buf(self.dev, np.uint32, 16, ipc=True)
+        check(lib.b200_memset_async(self.dev.idx, self.flags.ptr, 0, 64, queue.handle))
+        queue.wait()
+        self._opened = []
+        self.connected = False
+
+    def _field_bufs(self):
+        return self.bufs
+
+    def _plan_handle(self):
+        return self.plan
+
+    def window(self, global_field: np.ndarray) -> np.ndarray:
+        return self.tile.window(global_field)
+
+    def initial_field(self) -> np.ndarray:
+        import math
+
+        return math.exp(-math.pi * math.pi * 0.0) * (self.sx[None, :] + self.sy[:, None])
+
+    def upload(self, local_field: np.ndarray) -> None:
+        local_field = np.ascontiguousarray(local_field, dtype=np.float64)
+        if local_field.shape != self.tile.shape:
+            raise B200Error(-1, "deep heat tile: field must be (ny+2G) x (nx+2G)")
+        memcpy(self.queue, self.bufs[0], local_field)
+        memcpy(self.queue, self.bufs[1], local_field)
+        self.queue.wait()
+        self.cur = 0
+
+    def step(self, n: Optional[int] = None) -> None:
+        """n FTCS steps (default: one launch of `levels`) in launches of 4, 6 or 8 levels, none deeper than the ghost cells."""
+        G = self.levels
+        n = G if n is None else n
+        allowed = [d for d in (4, 6, 8) if d <= G]
+        # fewest launches out of the walker depths that fit
+        best = {0: []}
+        for k in range(1, n + 1):
+            cands = [best[k - d] + [d] for d in allowed if k - d in best]
+            if cands:
+                best[k] = min(cands, key=len)
+        if n not in best:
+            raise B200Error(-1, f"deep heat tile with ghost cells {G} deep: {n} steps cannot be covered by launches of {allowed} levels")
+        if not self.connected:
+            raise B200Error(-1, "HeatTileDeep.step before connect()")
+        lib = _lib.load()
+        for k in sorted(best[n], reverse=True):
+            self.launch_index += 1
+            tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
+            arr = (C.c_double * k)(*tfs)
+            check(lib.b200_heat2d_stepn_tile_f64(self.plan, self.queue.handle, self.cur, self.rx, self.ry, k, arr, self.launch_index))
+            self.step_index += k
+            self.cur ^= 1
+        self.queue._after_enqueue()
+
+    def download(self) -> np.ndarray:
+        out = np.empty(self.tile.shape, dtype=np.float64)
+        self.queue.wait()
+        memcpy(self.queue, out, self.bufs[self.cur])
+        self.queue.wait()
+        self.raise_on_timeout()
+        return out
+
+    def stitch(self, global_out: np.ndarray, local_field: np.ndarray) -> None:
+        self.tile.stitch(global_out, local_field)
+
+    def close(self) -> None:
+        self._close_peers()
+        if getattr(self, "plan", None):
+            _lib.load().b200_heat2d_plan_destroy(self.plan)
+            self.plan = None
+        for b in self.bufs:
+            b.free()
+        self.bufs = []
+        self.flags.free()
+
+
 def connect_over_process_group(tile_runner: HeatTile, dist) -> None:
     """One process per GPU: all-gather the IPC handles (objects, once) and map the neighbours' buffers."""
     world = dist.get_world_size()

@@ -402,6 +402,31 @@ extern "C"
         b200_heat2d_plan_t* out);
     int b200_heat2d_step2_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, double time_factor_1, double time_factor_2, uint32_t step);
     int b200_heat2d_stepn_halo_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors, uint32_t step);
+    /* ---- 2-D TILES with G = 4 .. 8 time levels per launch (new; closes the gap between the 2-D decomposition of
+     * b200_heat2d_step_halo_f64, one level per launch, and the row slabs above). Ghost cells G deep on all four sides:
+     * array (ny+2G) x (nx+2G) doubles, core cells [G, ny+G) x [G, nx+G), on a physical side the row / column next to them is
+     * the ring and the cells beyond are unused; sx_host has nx+2G entries, sy_host ny+2G (local indices, ghosts included);
+     * ny, nx >= 2G; all tiles of a field have the same extents and pitch. b200_heat2d_plan_set_halo wires up to four
+     * neighbours. One b200_heat2d_stepn_tile_f64 (levels = 4, 6 or 8 <= G; the walker kernel) is TWO launches: the step
+     * itself, whose strips store the first / last G core rows into the vertical neighbours' ghost rows and publish `step` in
+     * their row flags exactly as the slab form does; then a small column kernel that waits for the vertical neighbours' row
+     * flags of this step and stores the first / last G core columns -- over every row holding level data, the ghost rows just
+     * received included, so the corner blocks reach the diagonal neighbours through the vertical ones -- into the horizontal
+     * neighbours' ghost columns and publishes `step` in their column flags. The next step's walkers that touch ghost columns
+     * wait for those. `step` is the 1-based launch index. */
+    int b200_heat2d_tile_plan_create(
+        int dev,
+        double* u0,
+        double* u1,
+        size_t pitch_bytes,
+        uint32_t ny,
+        uint32_t nx,
+        double const* sx_host, /* nx+2*ghost */
+        double const* sy_host, /* ny+2*ghost */
+        int edges,
+        uint32_t ghost, /* G */
+        b200_heat2d_plan_t* out);
+    int b200_heat2d_stepn_tile_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors, uint32_t step);
     /* 0, or 1 + side of the first flag wait that timed out (a neighbour stopped making progress). Synchronous. */
     int b200_heat2d_halo_status(b200_heat2d_plan_t plan, uint32_t* status);
 

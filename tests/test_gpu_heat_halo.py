@@ -174,3 +174,93 @@ def test_slab_argument_errors(gpu):
             s.close()
     with pytest.raises(ab.B200Error):  # rows do not divide
         multi.HeatSlab(queue, 0, 3, 64, 64)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# 2-D tiles advanced 4, 6 or 8 time levels per launch (b200_heat2d_tile_plan_create / b200_heat2d_stepn_tile_f64): ghost
+# cells that deep on all four sides, rows exchanged inside the walker launch, columns (and through them the corners) by the
+# column kernel that follows it.
+def run_deep_tiles(ab, dev, NY, NX, grid, steps, u0, levels):
+    from alpaka_b200 import multi
+
+    world = grid[0] * grid[1]
+    queues = [ab.Queue(dev) for _ in range(world)]
+    runners = [multi.HeatTileDeep(q, r, world, NY, NX, levels=levels, grid=grid) for r, q in enumerate(queues)]
+    multi.connect_in_process(runners)
+    for r in runners:
+        r.upload(r.window(u0))
+    left = steps
+    while left > 0:  # launch by launch on every tile in turn (they wait for each other's flags)
+        k = levels if left >= levels else left
+        for r in runners:
+            r.step(k)
+        left -= k
+    for q in queues:
+        q.wait()
+    out = np.full((NY + 2, NX + 2), np.nan)
+    for r in runners:
+        assert r.status() == 0, "a flag wait timed out"
+        r.stitch(out, r.download())
+    for r in runners:
+        r.close()
+    return out
+
+
+# (Py, Px), tile rows, tile columns: tiles narrower than one 128-column window, tiles with interior windows, one column of
+# tiles (no column exchange), one row of tiles (no row exchange), the 4 x 2 grid of eight GPUs
+DEEP_TILE_CASES = [((2, 2), 40, 48), ((2, 2), 70, 300), ((1, 2), 64, 160), ((2, 1), 64, 160), ((4, 2), 32, 200), ((2, 4), 50, 130),
+                   ((3, 3), 33, 141), ((1, 1), 64, 64)]
+
+
+@pytest.mark.parametrize("rough", [False, True], ids=["analytic_field", "rough_field"])
+@pytest.mark.parametrize("levels", [4, 6, 8])
+@pytest.mark.parametrize("case", DEEP_TILE_CASES, ids=lambda c: f"{c[0][0]}x{c[0][1]}_tiles_of_{c[1]}x{c[2]}")
+def test_deep_tiles_equal_undecomposed(gpu, case, levels, rough):
+    ab, dev, _ = gpu
+    grid, ny, nx = case
+    NY, NX = ny * grid[0], nx * grid[1]
+    steps = 3 * levels
+    dx, dy, dt = ol.heat_params(NY, NX)
+    if rough:  # exercises every neighbour term across the tile borders and the corners (the analytic field is smooth)
+        u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=41).reshape(NY + 2, NX + 2)
+    else:
+        u0 = np.empty((NY + 2, NX + 2))
+        ol.oracle().orc_heat2d_init(P(u0), NY, NX, NX + 2, dx, dy)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    got = run_deep_tiles(ab, dev, NY, NX, grid, steps, u0, levels)
+    mask = np.ones_like(want, dtype=bool)  # corners are written by neither reference kernel (BoundaryKernel.hpp:63-84)
+    mask[0, 0] = mask[0, -1] = mask[-1, 0] = mask[-1, -1] = False
+    assert got[mask].tobytes() == want[mask].tobytes()
+
+
+def test_deep_tiles_mixed_depths_and_refusals(gpu):
+    """Ghost cells 8 deep: launches of 8, 6 and 4 levels can follow each other (18 = 8 + 6 + 4); step counts no combination
+    of walker depths covers are refused, and so are tiles smaller than two ghost depths."""
+    ab, dev, queue = gpu
+    from alpaka_b200 import multi
+
+    grid, ny, nx = (2, 2), 48, 150
+    NY, NX = ny * grid[0], nx * grid[1]
+    dx, dy, dt = ol.heat_params(NY, NX)
+    u0 = ol.fill("uniform_f64", (NY + 2) * (NX + 2), seed=43).reshape(NY + 2, NX + 2)
+    want = ol.orc_heat_run(u0, 1, 18, dx, dy, dt)
+    queues = [ab.Queue(dev) for _ in range(4)]
+    runners = [multi.HeatTileDeep(q, r, 4, NY, NX, levels=8, grid=grid) for r, q in enumerate(queues)]
+    multi.connect_in_process(runners)
+    for r in runners:
+        r.upload(r.window(u0))
+    for k in (8, 6, 4):
+        for r in runners:
+            r.step(k)
+    out = np.full((NY + 2, NX + 2), np.nan)
+    for r in runners:
+        r.stitch(out, r.download())
+    with pytest.raises(ab.B200Error):
+        runners[0].step(7)
+    for r in runners:
+        r.close()
+    mask = np.ones_like(want, dtype=bool)
+    mask[0, 0] = mask[0, -1] = mask[-1, 0] = mask[-1, -1] = False
+    assert out[mask].tobytes() == want[mask].tobytes()
+    with pytest.raises(ab.B200Error):
+        multi.HeatTileDeep(queue, 0, 4, 24, 24, levels=8, grid=(2, 2))
