@@ -195,6 +195,34 @@ def check_heat(R: Ranks, G) -> dict:
         if len(R.mine) > 1:
             ab.runtime.tune_set("heat.grid_cap", 0)
 
+    # ---- 2-D tiles with ghost cells 4 deep, four levels per launch (rows inside the launch, columns by the column kernel)
+    try:
+        deep = {r: multi.HeatTileDeep(R.queues[r], r, R.world, NY, NX, dt=dt, levels=4) for r in R.mine}
+    except ab.B200Error:
+        deep = None  # tiles smaller than two ghost depths at this world size
+    if deep is not None and steps % 4 == 0:
+        R.connect(deep, exchange=False)
+        for r in R.mine:
+            deep[r].upload(deep[r].window(u0))
+        R.barrier()
+        for _ in range(steps // 4):
+            for r in R.mine:
+                deep[r].step(4)
+        R.barrier()
+        parts = R.all_gather({r: (deep[r].tile, deep[r].download(), deep[r].status()) for r in R.mine})
+        got = np.full_like(want, np.nan)
+        for tile, local, status in parts:
+            if status != 0:
+                raise AssertionError(f"rank {tile.rank}: deep tile flag wait timed out")
+            tile.stitch(got, local)
+        if got[corners].tobytes() != want[corners].tobytes():
+            raise AssertionError("2-D tiles at four levels per launch differ from the undecomposed reference field")
+        t0 = deep[R.mine[0]].tile
+        out[f"heat_tiles_{t0.py}x{t0.px}_4_levels"] = "bit-exact"
+        R.barrier()
+        for r in R.mine:
+            deep[r].close()
+
     # ---- row slabs, 2 / 3 / 4 / 6 / 8 levels per launch and per exchange (4, 6, 8: the walker kernel)
     for levels in (2, 3, 4, 6, 8):
         slabs = {r: multi.HeatSlab(R.queues[r], r, R.world, NY, NX, dt=dt, levels=levels) for r in R.mine}

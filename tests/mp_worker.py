@@ -127,6 +127,31 @@ def main():
             assert out.tobytes() == want_s.tobytes(), f"slab-decomposed {levels}-level heat differs from the undecomposed oracle"
         dist.barrier()
         slab.close()
+    # ---- 2-D tiles, 4 and 8 time levels per launch (ghost cells that deep on all sides; rows inside the walker launch, columns
+    # and corners by the column kernel), IPC peer pointers
+    NYd, NXd, steps3 = 96 * py, 320 * px, 24
+    dxd, dyd, dtd = ol.heat_params(NYd, NXd)
+    u0d = ol.fill("uniform_f64", (NYd + 2) * (NXd + 2), seed=77).reshape(NYd + 2, NXd + 2)
+    want_d = ol.orc_heat_run(u0d, 1, steps3, dxd, dyd, dtd) if rank == 0 else None
+    for levels in (4, 8):
+        deep = multi.HeatTileDeep(q, rank, world, NYd, NXd, levels=levels)
+        multi.connect_over_process_group(deep, dist)
+        deep.upload(deep.window(u0d))
+        dist.barrier()
+        deep.step(steps3)
+        q.wait()
+        assert deep.status() == 0, f"rank {rank}: deep tile flag wait timed out"
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((deep.tile, deep.download()), gathered, dst=0)
+        if rank == 0:
+            out = np.full((NYd + 2, NXd + 2), np.nan)
+            for tl, f in gathered:
+                tl.stitch(out, f)
+            mask = np.ones_like(want_d, dtype=bool)
+            mask[0, 0] = mask[0, -1] = mask[-1, 0] = mask[-1, -1] = False
+            assert out[mask].tobytes() == want_d[mask].tobytes(), f"2-D tiles at {levels} levels per launch differ from the undecomposed oracle"
+        dist.barrier()
+        deep.close()
     # ---- every sharded path against the committed golden vectors of the UNMODIFIED reference (tests/golden_multi.py;
     # the same block runs inside bench.py's N > 1 arm)
     import golden_multi

@@ -379,3 +379,34 @@ def test_slab_geometry_properties(world, ghost, rows_per_ghost, NX, data):
         back = range(t.g0 + t.send_rows("top").start, t.g0 + t.send_rows("top").stop)
         here = range(s.g0 + s.recv_rows("bottom").start, s.g0 + s.recv_rows("bottom").stop)
         assert list(back) == list(here)
+
+
+@settings(max_examples=200, deadline=None)
+@given(py=st.integers(1, 4), px=st.integers(1, 4), ghost=st.sampled_from([4, 6, 8]), ky=st.integers(2, 5), kx=st.integers(2, 5))
+def test_deep_tile_geometry_properties(py, px, ghost, ky, kx):
+    """decomp.deep_tile_for: the windows of a global field, stitched back from every tile's OWNED cells, give the field
+    again exactly once; ghost cells on a neighbour side are the neighbour's border core cells."""
+    ny, nx = ghost * ky, ghost * kx
+    NY, NX, world = ny * py, nx * px, py * px
+    g = np.arange((NY + 2) * (NX + 2), dtype=np.float64).reshape(NY + 2, NX + 2)
+    out = np.full_like(g, np.nan)
+    count = np.zeros_like(g)
+    tiles = [decomp.deep_tile_for(r, world, NY, NX, ghost, (py, px)) for r in range(world)]
+    for t in tiles:
+        w = t.window(g)
+        assert w.shape == (ny + 2 * ghost, nx + 2 * ghost)
+        t.stitch(out, w)
+        j0, j1, i0, i1 = t.owned()
+        count[t.gj0 + j0 : t.gj0 + j1, t.gi0 + i0 : t.gi0 + i1] += 1
+        # the top ghost rows of a tile with an upper neighbour are that neighbour's last `ghost` core rows
+        up = t.neighbours["top"]
+        if up is not None:
+            wu = tiles[up].window(g)
+            assert np.array_equal(w[0:ghost, ghost:-ghost], wu[ny : ny + ghost, ghost:-ghost])
+        left = t.neighbours["left"]
+        if left is not None:
+            wl = tiles[left].window(g)
+            assert np.array_equal(w[:, 0:ghost], wl[:, nx : nx + ghost])
+    assert np.array_equal(out, g) and np.all(count == 1)
+    with pytest.raises(ValueError):
+        decomp.deep_tile_for(0, world, NY, NX, max(ny, nx))  # tiles smaller than two ghost depths
