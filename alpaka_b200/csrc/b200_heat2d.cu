@@ -1451,6 +1451,7 @@ namespace
         double* peer[2]; // [left, right] neighbour's same buffer, or null
         uint32_t* peerFlag[2]; // their flag word for my side
         uint32_t const* rowFlags[2]; // my flag words set by the top / bottom neighbour's launch, or null
+        uint32_t const* colFlags[2]; // my flag words set by the left / right neighbour's column kernel; waited for at the END
         uint32_t* counter; // blocks finished (reset by the last one)
         uint32_t* status;
         uint64_t waitNs;
@@ -1495,6 +1496,13 @@ namespace
                 for(int side = 0; side < 2; ++side)
                     if(A.peerFlag[side] != nullptr)
                         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(A.peerFlag[side]), "r"(A.step) : "memory");
+                // ... and stay until the horizontal neighbours' columns of this launch have arrived here: the kernel is the
+                // pairwise barrier of the column exchange, so the next walker launch starts with its ghost columns complete
+                // and none of its walkers has to wait for them (waiting inside the walker cost 150 us per launch on two GPUs,
+                // profiles/r02/heat_deep_probe_n2.log)
+                for(int side = 0; side < 2; ++side)
+                    if(A.colFlags[side] != nullptr && !b200::waitFlagAtLeast(A.colFlags[side], A.step, 0u, A.waitNs))
+                        atomicExch(A.status, 3u + uint32_t(side));
             }
         }
     }
@@ -1672,7 +1680,7 @@ namespace
         A.ghostLeft = (plan->edges & B200_EDGE_LEFT) ? 0 : 1;
         A.ghostRight = (plan->edges & B200_EDGE_RIGHT) ? 0 : 1;
         A.colFlags[0] = A.colFlags[1] = nullptr;
-        if(A.myFlags != nullptr && plan->padX > 1)
+        if(A.myFlags != nullptr && plan->padX > 1 && b200::tune("heat.tile_wait_in_walker", 0) != 0)
         {
             // 2-D tile: the ghost columns arrive by the column exchange that follows every launch (haloColsKernel)
             if(A.ghostLeft)
@@ -2528,12 +2536,20 @@ extern "C"
         H.peerFlag[1] = right ? plan->halo.peer_flag[3] : nullptr;
         H.rowFlags[0] = top ? plan->halo.my_flags + 0 : nullptr;
         H.rowFlags[1] = bottom ? plan->halo.my_flags + 1 : nullptr;
+        bool const waitHere = b200::tune("heat.tile_wait_in_walker", 0) == 0;
+        H.colFlags[0] = left && waitHere ? plan->halo.my_flags + 2 : nullptr;
+        H.colFlags[1] = right && waitHere ? plan->halo.my_flags + 3 : nullptr;
         H.counter = plan->haloScratch + 2;
         H.status = plan->haloScratch + 1;
         H.waitNs = b200::waitLimitNs();
         H.step = step;
-        if(b200::tune("heat.halo_debug", 0) & 2)
-            H.rowFlags[0] = H.rowFlags[1] = nullptr;
+        int64_t const dbg = b200::tune("heat.halo_debug", 0);
+        if(dbg & 2)
+            H.rowFlags[0] = H.rowFlags[1] = H.colFlags[0] = H.colFlags[1] = nullptr;
+        if(dbg & 1)
+            H.peer[0] = H.peer[1] = nullptr; // (the flags are still published)
+        if(dbg & 4)
+            return 0; // measurement only: no column kernel at all (the next launch must run with bit 2 set)
         int64_t const cells = 2 * (int64_t(H.rowHi) - H.rowLo + 1) * G;
         unsigned const grid = unsigned(std::min<int64_t>(64, (cells + 255) / 256));
         haloColsKernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(H);
