@@ -245,13 +245,14 @@ def deep_tile_for(rank: int, world: int, NY: int, NX: int, ghost: int, grid: Opt
 SUPPORTED_DEPTHS = (1, 2, 3, 4, 6, 8)
 
 
-def launch_schedule(n: int, depth: int, min_depth: int = 1) -> list[int]:
+def launch_schedule(n: int, depth: int, min_depth: int = 1, depths: tuple = SUPPORTED_DEPTHS) -> list[int]:
     """Time levels per launch for n steps with at most `depth` levels per launch, out of the depths the kernels support
-    (SUPPORTED_DEPTHS): the fewest launches, and among those schedules the one whose shallowest launch is deepest
-    (4 = 2 + 2 rather than 3 + 1), deep launches first. min_depth = 2 for slabs, which cannot advance a single level."""
+    (`depths`, by default SUPPORTED_DEPTHS; deep 2-D tiles: the walker's 4, 6, 8): the fewest launches, and among those
+    schedules the one whose shallowest launch is deepest (4 = 2 + 2 rather than 3 + 1), deep launches first. min_depth = 2
+    for slabs, which cannot advance a single level."""
     if n < 0 or depth < max(1, min_depth):
         raise ValueError("launch_schedule: bad arguments")
-    allowed = [d for d in SUPPORTED_DEPTHS if min_depth <= d <= depth]
+    allowed = [d for d in depths if min_depth <= d <= depth]
     if not allowed:
         raise ValueError(f"no supported launch depth in {min_depth}..{depth}")
     top = allowed[-1]

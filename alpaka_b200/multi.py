@@ -351,19 +351,14 @@ class HeatTileDeep(_HaloWiring):
         """n FTCS steps (default: one launch of `levels`) in launches of 4, 6 or 8 levels, none deeper than the ghost cells."""
         G = self.levels
         n = G if n is None else n
-        allowed = [d for d in (4, 6, 8) if d <= G]
-        # fewest launches out of the walker depths that fit
-        best = {0: []}
-        for k in range(1, n + 1):
-            cands = [best[k - d] + [d] for d in allowed if k - d in best]
-            if cands:
-                best[k] = min(cands, key=len)
-        if n not in best:
-            raise B200Error(-1, f"deep heat tile with ghost cells {G} deep: {n} steps cannot be covered by launches of {allowed} levels")
+        try:
+            schedule = decomp.launch_schedule(n, G, min_depth=4, depths=(4, 6, 8))
+        except ValueError as e:
+            raise B200Error(-1, f"deep heat tile with ghost cells {G} deep: {e}") from None
         if not self.connected:
             raise B200Error(-1, "HeatTileDeep.step before connect()")
         lib = _lib.load()
-        for k in sorted(best[n], reverse=True):
+        for k in schedule:
             self.launch_index += 1
             tfs = [heat2d.time_factor(self.step_index + 1 + l, self.dt) for l in range(k)]
             arr = (C.c_double * k)(*tfs)

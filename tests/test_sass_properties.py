@@ -39,6 +39,27 @@ def test_stencil_tiles_arrive_by_tma_and_levels_exchange_by_shuffle():
     assert "SYNCS" in text or "MBARRIER" in text.upper()  # mbarrier-signalled copies
 
 
+def test_walker_kernel_loads_by_tma_stores_256_bits_and_exchanges_by_shuffle():
+    """heatWalkKernel (the default instantiation at four levels): its stages arrive by TMA (UTMALDG.2D), the quad of a lane
+    leaves by one 256-bit store, products travel between lanes by SHFL, there is no CTA-wide barrier (BAR.SYNC) in it, and the
+    DP instructions are plain DMUL / DADD (contraction off)."""
+    path = os.path.join(OBJ, "b200_heat2d.o")
+    if not os.path.exists(path) or not os.path.exists(CUOBJDUMP):
+        pytest.skip(f"{path} or cuobjdump missing")
+    text = subprocess.run([CUOBJDUMP, "-sass", "-fun", "heatWalkKernel", path], capture_output=True, text=True).stdout
+    if "Function" not in text:  # older cuobjdump: no substring match for -fun; cut the functions out of the full dump
+        full = sass("b200_heat2d")
+        text = "\n".join(blk for blk in full.split("Function : ") if blk.startswith("_ZN") and "heatWalkKernelILi4ELi4ELi4ELb1ELi3ELb0ELb0E" in blk.split("\n")[0])
+    else:
+        text = "\n".join(blk for blk in text.split("Function : ") if "heatWalkKernelILi4ELi4ELi4ELb1ELi3ELb0ELb0E" in blk.split("\n")[0])
+    assert text, "default walker instantiation not found"
+    assert "UTMALDG.2D" in text and "SYNCS" in text
+    assert re.search(r"STG\.E[.\w]*\.256", text)
+    assert "SHFL.UP" in text and "SHFL.DOWN" in text
+    assert "BAR.SYNC" not in text, "the walker must not synchronise CTA-wide"
+    assert text.count("DADD") > 100 and text.count("DMUL") > 50 and not re.search(r"\bDFMA\b", text)
+
+
 def test_streams_use_32_byte_vector_accesses():
     text = sass("b200_stream")
     assert re.search(r"LDG\.E[.\w]*\.256", text) and re.search(r"STG\.E[.\w]*\.256", text)
@@ -63,7 +84,9 @@ def ptxas_entries(name):
     ("b200_stream", ["TriadOpIdEEdLi32ELi1ELi1E", "CopyOpIdEEdLi32ELi1ELi1E", "NstreamOpIdEEdLi32ELi1ELi1E"]),
     ("b200_reduce", ["reduceKernelIdLb1ELi2E", "reduceKernelIjLb0ELi4E", "reduceKernelIfLb0ELi4E"]),
     ("b200_heat2d", ["heatStepKernelILi1ELi8E", "heatStep2KernelILi1ELi64ELi16E", "heatStepNKernelILi4ELi16ELi2ELb1ELi4E", "heatStepNKernelILi4ELi16ELi2ELb0ELi4E",
-                     "heatStepNKernelILi3ELi16ELi2ELb1ELi4E"]),
+                     "heatStepNKernelILi3ELi16ELi2ELb1ELi4E",
+                     # the walker kernel's default instantiations: 4 levels (168 registers), 6 and 8 levels (255), square cells
+                     "heatWalkKernelILi4ELi4ELi4ELb1ELi3ELb0ELb0E", "heatWalkKernelILi6ELi4ELi4ELb1ELi2ELb0ELb0E"]),
 ])
 def test_default_instantiations_do_not_spill(obj, needles):
     entries = ptxas_entries(obj)
@@ -72,6 +95,26 @@ def test_default_instantiations_do_not_spill(obj, needles):
         assert hits, f"no entry function matching {needle} in {obj}"
         for k, (stack, st, ld) in hits.items():
             assert (stack, st, ld) == (0, 0, 0), f"{k}: {stack} bytes stack, {st}/{ld} bytes spilled"
+
+
+def test_eight_level_walker_spills_only_outside_its_bare_loop():
+    """heatWalkKernel<8, ...> sits at the 255-register ceiling; the few words it spills (integer loop constants) must be
+    reloaded in the edge-window and careful paths only: between the first pair of LDS.128 and the fourth 256-bit store after
+    it -- the four unrolled rows of the bare chunk -- there is no local-memory access."""
+    entries = ptxas_entries("b200_heat2d")
+    hits = {k: v for k, v in entries.items() if "heatWalkKernelILi8ELi4ELi4ELb1ELi2ELb0ELb0E" in k}
+    assert hits
+    for k, (stack, st, ld) in hits.items():
+        assert stack <= 96, f"{k}: {stack} bytes of stack"
+    full = sass("b200_heat2d")
+    blocks = [b for b in full.split("Function : ") if "heatWalkKernelILi8ELi4ELi4ELb1ELi2ELb0ELb0E" in b.split("\n")[0]]
+    assert blocks
+    lines = blocks[0].splitlines()
+    first = next(i for i, l in enumerate(lines) if "LDS.128" in l)
+    stores = [i for i, l in enumerate(lines) if i > first and re.search(r"STG\.E[.\w]*\.256", l)]
+    assert len(stores) >= 4
+    bare = "\n".join(lines[first:stores[3] + 1])
+    assert "LDL" not in bare and "STL" not in bare, "the bare loop of the eight-level walker touches local memory"
 
 
 def test_block_and_grid_hierarchy_atomics_have_device_scope():
