@@ -12,6 +12,8 @@
 //   --mode=fused2     per TWO steps: one launch that keeps the intermediate time level in registers
 //   --mode=fused3 / fused4 / fused6 / fused8   per THREE / FOUR / SIX / EIGHT steps: likewise (Heat2DStepper::steps -> b200_heat2d_step2_f64 / b200_heat2d_stepn_f64;
 //                     a remainder runs in shallower launches); same bits
+//   --mode=tiles      --py=Py --px=Px tiles of the field in this process, tile r on device r % (number of devices), --levels=G
+//                     (4, 6, 8) time levels per launch, ghost cells G deep on all sides (alpaka::b200::Heat2DTiles); same bits
 //   --mode=slabs      --slabs=K row slabs of the field in this process, slab k on device k % (number of devices), --levels=G
 //                     (2, 3, 4, 6, 8) time levels per launch and per ghost-row exchange (alpaka::b200::Heat2DSlabs); same bits
 //   --ny --nx --steps --dt-factor (dt = factor * min(dx^2, dy^2), default 0.2; stability needs <= 0.25)
@@ -206,6 +208,31 @@ auto main(int argc, char** argv) -> int
                       << ", \"gbs\": " << 16.0 * double(ny) * double(nx) * numTimeSteps * 1e-9 / secs << ", \"max_error\": " << errSlabs << "}" << std::endl;
             std::cout << (okSlabs ? "Execution results correct!" : "Execution results incorrect!") << std::endl;
             return okSlabs ? EXIT_SUCCESS : EXIT_FAILURE;
+        }
+        else if(mode == "tiles")
+        {
+            auto const Py = static_cast<unsigned>(args.u64("py", 2)), Px = static_cast<unsigned>(args.u64("px", 2));
+            auto const nDev = static_cast<unsigned>(alpaka::getDevCount(alpaka::Platform<Acc>{}));
+            std::vector<alpaka::DevB200> devs;
+            for(unsigned k = 0; k < Py * Px; ++k)
+                devs.push_back(alpaka::getDevByIdx(alpaka::Platform<Acc>{}, k % nDev));
+            alpaka::b200::Heat2DTiles tiles(devs, Py, Px, ny, nx, dx, dy, dt, static_cast<int>(args.u64("levels", 4)));
+            tiles.upload(uBufHost.data());
+            auto const ts = std::chrono::high_resolution_clock::now();
+            tiles.steps(numTimeSteps);
+            tiles.waitAll();
+            double const secs = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - ts).count();
+            tiles.download(uBufHost.data()); // owned cells of every tile; the corners keep their initial values
+            auto const [okTiles, errTiles] = validateSolution(uBufHost, extent, dx, dy, tMax);
+            if(args.has("output"))
+                cli::writeFile(args.str("output"), uBufHost.data(), sizeof(double) * std::size_t(extent[0]) * extent[1]);
+            std::cout << "{\"driver\": \"heat2d_b200\", \"mode\": \"tiles\", \"py\": " << Py << ", \"px\": " << Px
+                      << ", \"devices\": " << (Py * Px < nDev ? Py * Px : nDev) << ", \"ny\": " << ny << ", \"nx\": " << nx
+                      << ", \"steps\": " << numTimeSteps << ", \"launches\": " << tiles.launches() << ", \"seconds\": " << secs
+                      << ", \"ms_per_step\": " << secs * 1e3 / numTimeSteps
+                      << ", \"gbs\": " << 16.0 * double(ny) * double(nx) * numTimeSteps * 1e-9 / secs << ", \"max_error\": " << errTiles << "}" << std::endl;
+            std::cout << (okTiles ? "Execution results correct!" : "Execution results incorrect!") << std::endl;
+            return okTiles ? EXIT_SUCCESS : EXIT_FAILURE;
         }
         else
         {

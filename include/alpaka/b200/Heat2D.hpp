@@ -381,4 +381,238 @@ namespace alpaka::b200
         int m_cur = 0;
         std::uint32_t m_step = 0, m_launch = 0;
     };
+    //! Py x Px TILES of ONE heat field driven from one host thread, advanced `levels` (4, 6 or 8) time levels per launch: the
+    //! C++ form of alpaka_b200.multi.HeatTileDeep. Tile r = cy * Px + cx lives on devs[r] (devices may repeat). Ghost cells
+    //! `levels` deep on all four sides; per launch the rows travel inside the walker kernel and the columns (with the
+    //! corners) in the column kernel that follows it (b200_heat2d_tile_plan_create / b200_heat2d_stepn_tile_f64).
+    //! Host fields are (NY+2) x (NX+2) doubles, rows unpadded, as the reference driver's host buffer.
+    class Heat2DTiles
+    {
+    public:
+        using Idx = std::uint32_t;
+        using Buf2 = BufB200<double, DimInt<2u>, Idx>;
+        using BufFlags = BufB200<std::uint32_t, DimInt<1u>, Idx>;
+        using Queue = QueueB200<NonBlocking>;
+
+        Heat2DTiles(std::vector<DevB200> const& devs, Idx Py, Idx Px, Idx NY, Idx NX, double dx, double dy, double dt, int levels = 4)
+            : m_NY(NY)
+            , m_NX(NX)
+            , m_Py(Py)
+            , m_Px(Px)
+            , m_G(static_cast<Idx>(levels))
+            , m_dt(dt)
+            , m_rX(dt / (dx * dx))
+            , m_rY(dt / (dy * dy))
+        {
+            if(Py == 0 || Px == 0 || devs.size() != static_cast<std::size_t>(Py) * Px || !(levels == 4 || levels == 6 || levels == 8)
+               || NY % Py != 0 || NX % Px != 0 || NY / Py < 2 * m_G || NX / Px < 2 * m_G)
+                throw std::runtime_error(
+                    "Heat2DTiles: one device per tile, NY x NX must divide into tiles of at least 2*levels cells per side, levels 4, 6 or 8");
+            m_ny = NY / Py;
+            m_nx = NX / Px;
+            bool distinct = false;
+            for(auto const& d : devs)
+                distinct = distinct || d.getNativeHandle() != devs[0].getNativeHandle();
+            if(distinct)
+            {
+                int pairs = 0;
+                check(b200_enable_peer_all(&pairs));
+            }
+            constexpr double pi = math::constants::pi;
+            auto const K = Py * Px;
+            m_tiles.reserve(K);
+            for(Idx r = 0; r < K; ++r)
+            {
+                Idx const cy = r / Px, cx = r % Px;
+                Vec<DimInt<2u>, Idx> const ext{m_ny + 2u * m_G, m_nx + 2u * m_G};
+                Tile t{devs[r], Queue{devs[r]}, allocBuf<double, Idx>(devs[r], ext), allocBuf<double, Idx>(devs[r], ext),
+                       allocBuf<std::uint32_t, Idx>(devs[r], Vec<DimInt<1u>, Idx>{16u}), nullptr,
+                       static_cast<std::int64_t>(cy) * m_ny - (static_cast<std::int64_t>(m_G) - 1),
+                       static_cast<std::int64_t>(cx) * m_nx - (static_cast<std::int64_t>(m_G) - 1),
+                       (cy == 0 ? B200_EDGE_TOP : 0) | (cy == Py - 1 ? B200_EDGE_BOTTOM : 0) | (cx == 0 ? B200_EDGE_LEFT : 0)
+                           | (cx == Px - 1 ? B200_EDGE_RIGHT : 0)};
+                alpaka::memset(t.queue, t.flags, 0);
+                alpaka::memset(t.queue, t.u[0], 0);
+                alpaka::memset(t.queue, t.u[1], 0);
+                std::vector<double> sx(ext[1]), sy(ext[0]);
+                for(Idx i = 0; i < ext[1]; ++i)
+                    sx[i] = std::sin(pi * (static_cast<double>(t.gi0 + static_cast<std::int64_t>(i)) * dx));
+                for(Idx j = 0; j < ext[0]; ++j)
+                    sy[j] = std::sin(pi * (static_cast<double>(t.gj0 + static_cast<std::int64_t>(j)) * dy));
+                check(b200_heat2d_tile_plan_create(
+                    devs[r].getNativeHandle(),
+                    std::data(t.u[0]),
+                    std::data(t.u[1]),
+                    static_cast<std::size_t>(getPitchesInBytes(t.u[0])[0]),
+                    m_ny,
+                    m_nx,
+                    sx.data(),
+                    sy.data(),
+                    t.edges,
+                    m_G,
+                    &t.plan));
+                m_tiles.push_back(std::move(t));
+            }
+            for(Idx r = 0; r < K; ++r)
+            {
+                Idx const cy = r / Px, cx = r % Px;
+                b200_heat2d_halo halo{};
+                // side 0 top, 1 bottom, 2 left, 3 right; the neighbour's flag slot is the one for the OPPOSITE side
+                auto const wire = [&](int side, Idx nb, int opposite)
+                {
+                    halo.peer_u[side][0] = std::data(m_tiles[nb].u[0]);
+                    halo.peer_u[side][1] = std::data(m_tiles[nb].u[1]);
+                    halo.peer_flag[side] = std::data(m_tiles[nb].flags) + opposite;
+                };
+                if(cy > 0)
+                    wire(0, r - Px, 1);
+                if(cy + 1 < Py)
+                    wire(1, r + Px, 0);
+                if(cx > 0)
+                    wire(2, r - 1, 3);
+                if(cx + 1 < Px)
+                    wire(3, r + 1, 2);
+                halo.my_flags = std::data(m_tiles[r].flags);
+                wait(m_tiles[r].queue);
+                check(b200_heat2d_plan_set_halo(m_tiles[r].plan, &halo));
+            }
+        }
+        Heat2DTiles(Heat2DTiles const&) = delete;
+        auto operator=(Heat2DTiles const&) -> Heat2DTiles& = delete;
+        ~Heat2DTiles()
+        {
+            for(auto& t : m_tiles)
+            {
+                try
+                {
+                    wait(t.queue);
+                }
+                catch(...)
+                {
+                }
+                checkNoexcept(b200_heat2d_plan_destroy(t.plan));
+            }
+        }
+
+        //! every tile's window of the host field (ghost cells included; cells outside the field stay 0) into both buffers
+        void upload(double const* hostField)
+        {
+            for(auto& t : m_tiles)
+                for(int b = 0; b < 2; ++b)
+                    copyBlock(t, b, 0, m_ny + 2u * m_G, 0, m_nx + 2u * m_G, const_cast<double*>(hostField), B200_COPY_H2D);
+            waitAll();
+            m_cur = 0;
+        }
+
+        //! `n` steps in launches of 8, 6 or 4 levels, none deeper than the ghost cells; n must be coverable (e.g. a multiple of 4)
+        void steps(std::uint32_t n)
+        {
+            constexpr double pi = math::constants::pi;
+            while(n > 0)
+            {
+                std::uint32_t k = 0;
+                for(std::uint32_t d : {8u, 6u, 4u})
+                    if(d <= m_G && d <= n && (n - d == 0 || n - d >= 4) && (n - d) % 2 == 0)
+                    {
+                        k = d;
+                        break;
+                    }
+                if(k == 0)
+                    throw std::runtime_error("Heat2DTiles::steps: the remaining steps cannot be covered by launches of 4, 6 or 8 levels");
+                double tf[8] = {};
+                for(Idx l = 0; l < k; ++l)
+                    tf[l] = std::exp(-pi * pi * ((m_step + 1u + l) * m_dt));
+                ++m_launch;
+                for(auto& t : m_tiles)
+                {
+                    check(b200_heat2d_stepn_tile_f64(t.plan, t.queue.getNativeHandle(), m_cur, m_rX, m_rY, static_cast<int>(k), tf, m_launch));
+                    t.queue.afterEnqueue();
+                }
+                m_step += k;
+                m_cur ^= 1;
+                n -= k;
+            }
+        }
+
+        //! the cells every tile OWNS (core cells, plus the physical ring on boundary sides) into the host field
+        void download(double* hostField)
+        {
+            waitAll();
+            for(auto& t : m_tiles)
+            {
+                Idx const j0 = (t.edges & B200_EDGE_TOP) ? m_G - 1u : m_G, j1 = (t.edges & B200_EDGE_BOTTOM) ? m_ny + m_G + 1u : m_ny + m_G;
+                Idx const i0 = (t.edges & B200_EDGE_LEFT) ? m_G - 1u : m_G, i1 = (t.edges & B200_EDGE_RIGHT) ? m_nx + m_G + 1u : m_nx + m_G;
+                copyBlock(t, m_cur, j0, j1, i0, i1, hostField, B200_COPY_D2H);
+            }
+            waitAll();
+            for(auto& t : m_tiles)
+            {
+                std::uint32_t status = 0;
+                check(b200_heat2d_halo_status(t.plan, &status));
+                if(status != 0)
+                    throw std::runtime_error("Heat2DTiles: a neighbour's flag never arrived (side " + std::to_string(status - 1) + ")");
+            }
+        }
+
+        void waitAll()
+        {
+            for(auto& t : m_tiles)
+                wait(t.queue);
+        }
+
+        [[nodiscard]] auto stepsDone() const -> std::uint32_t
+        {
+            return m_step;
+        }
+        [[nodiscard]] auto launches() const -> std::uint32_t
+        {
+            return m_launch;
+        }
+
+    private:
+        struct Tile
+        {
+            DevB200 dev;
+            Queue queue;
+            Buf2 u[2];
+            BufFlags flags;
+            b200_heat2d_plan_t plan;
+            std::int64_t gj0, gi0; // global padded row / column of local cell (0, 0)
+            int edges;
+        };
+
+        //! local cells [j0, j1) x [i0, i1) of array `b` <-> the same global cells of the host field, clipped to the field
+        void copyBlock(Tile& t, int b, Idx j0, Idx j1, Idx i0, Idx i1, double* hostField, int kind)
+        {
+            auto const clip = [](std::int64_t v, std::int64_t hi) { return v < 0 ? std::int64_t{0} : (v > hi ? hi : v); };
+            std::int64_t const jl = clip(t.gj0 + j0, static_cast<std::int64_t>(m_NY) + 2), jh = clip(t.gj0 + j1, static_cast<std::int64_t>(m_NY) + 2);
+            std::int64_t const il = clip(t.gi0 + i0, static_cast<std::int64_t>(m_NX) + 2), ih = clip(t.gi0 + i1, static_cast<std::int64_t>(m_NX) + 2);
+            if(jl >= jh || il >= ih)
+                return;
+            auto const pitch = static_cast<std::size_t>(getPitchesInBytes(t.u[b])[0]);
+            auto* const devPtr = reinterpret_cast<char*>(std::data(t.u[b])) + static_cast<std::size_t>(jl - t.gj0) * pitch
+                                 + static_cast<std::size_t>(il - t.gi0) * sizeof(double);
+            double* const hostPtr = hostField + static_cast<std::size_t>(jl) * (m_NX + 2u) + static_cast<std::size_t>(il);
+            std::size_t const hostPitch = (static_cast<std::size_t>(m_NX) + 2u) * sizeof(double);
+            std::size_t const rowBytes = static_cast<std::size_t>(ih - il) * sizeof(double);
+            void* const dst = kind == B200_COPY_H2D ? static_cast<void*>(devPtr) : static_cast<void*>(hostPtr);
+            void const* const src = kind == B200_COPY_H2D ? static_cast<void const*>(hostPtr) : static_cast<void const*>(devPtr);
+            check(b200_memcpy2d_async(
+                t.dev.getNativeHandle(),
+                dst,
+                kind == B200_COPY_H2D ? pitch : hostPitch,
+                src,
+                kind == B200_COPY_H2D ? hostPitch : pitch,
+                rowBytes,
+                static_cast<std::size_t>(jh - jl),
+                kind,
+                t.queue.getNativeHandle()));
+        }
+
+        Idx m_NY, m_NX, m_Py, m_Px, m_G, m_ny = 0, m_nx = 0;
+        double m_dt, m_rX, m_rY;
+        std::vector<Tile> m_tiles;
+        int m_cur = 0;
+        std::uint32_t m_step = 0, m_launch = 0;
+    };
 } // namespace alpaka::b200

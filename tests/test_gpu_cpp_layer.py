@@ -285,6 +285,27 @@ def test_heat2d_cpp_slabs_vs_oracle(tmp_path, slabs, shape, levels):
     assert last_json(r.stdout)["launches"] == len(__import__("alpaka_b200").decomp.launch_schedule(steps, levels, 2))
 
 
+@pytest.mark.parametrize("levels", [4, 8])
+@pytest.mark.parametrize("grid,shape", [((2, 2), (96, 320)), ((1, 2), (64, 300)), ((3, 1), (120, 140)), ((2, 3), (64, 480))])
+def test_heat2d_cpp_tiles_vs_oracle(tmp_path, grid, shape, levels):
+    """alpaka::b200::Heat2DTiles: Py x Px tiles in one process (here all on device 0), ghost cells `levels` deep on all sides,
+    rows exchanged inside the walker launch and columns + corners by the column kernel. Bit-exact against the undecomposed
+    oracle (corners excepted: neither reference kernel writes them)."""
+    ny, nx = shape
+    steps = 24
+    dx, dy, dt = ol.heat_params(ny, nx)
+    out = tmp_path / "u.bin"
+    r = run("heat2d_b200", f"--ny={ny}", f"--nx={nx}", f"--steps={steps}", f"--dt={dt!r}", "--mode=tiles", f"--py={grid[0]}",
+            f"--px={grid[1]}", f"--levels={levels}", f"--output={out}", check=False)
+    assert os.path.exists(out), r.stdout + r.stderr
+    got = np.fromfile(out, dtype=np.float64).reshape(ny + 2, nx + 2)
+    u0 = np.empty((ny + 2, nx + 2))
+    ol.oracle().orc_heat2d_init(P(u0), ny, nx, nx + 2, dx, dy)
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    assert got.tobytes() == want.tobytes()  # (the driver's host field keeps the initial corners, as the oracle's does)
+    assert last_json(r.stdout)["launches"] == 24 // levels
+
+
 def test_heat2d_cpp_slabs_on_several_devices(tmp_path):
     """The same with one slab per DEVICE of this process (peer stores over NVLink into the other device's pool memory:
     b200_enable_peer_all grants the pools' access). Needs >= 2 devices."""
