@@ -78,6 +78,18 @@ class Heat2dHalo(C.Structure):
     ]
 
 
+class Heat2dWalkPlan(C.Structure):
+    """b200_heat2d_walk_plan: the host-side decomposition of a walker launch (b200_heat2d_walk_plan_query)."""
+
+    _fields_ = [
+        ("window_columns", C.c_uint32), ("n_windows", C.c_uint32), ("n_edge_right", C.c_uint32),
+        ("n_front", C.c_uint32), ("front_is_strip", C.c_uint32),
+        ("front_y0", C.c_int32 * 2), ("front_y1", C.c_int32 * 2),
+        ("interior_y0", C.c_int32), ("interior_y1", C.c_int32), ("segment_rows", C.c_int32),
+        ("n_segments", C.c_uint32), ("n_walkers", C.c_uint32), ("split", C.c_int32),
+    ]
+
+
 class Exchange(C.Structure):
     """b200_exchange: every rank's exchange buffer as seen from this device (fused Dot / reduce over several GPUs)."""
 
@@ -179,6 +191,7 @@ SIGNATURES: dict[str, list] = {
     "b200_heat2d_stepn_halo_f64": [_vp, _vp, _i, _f64, _f64, _i, _vp, _u32],
     "b200_heat2d_tile_plan_create": [_i, _vp, _vp, _sz, _u32, _u32, _vp, _vp, _i, _u32, _P(_vp)],
     "b200_heat2d_stepn_tile_f64": [_vp, _vp, _i, _f64, _f64, _i, _vp, _u32],
+    "b200_heat2d_walk_plan_query": [_u32, _u32, _u32, _u32, _i, _i, _i, _vp],
     "b200_heat2d_step2_halo_f64": [_vp, _vp, _i, _f64, _f64, _f64, _f64, _u32],
     "b200_heat2d_step_window_f64": [_vp, _vp, _i, _f64, _f64, _f64, _u32, _u32, _u32, _u32],
     "b200_heat2d_boundary_f64": [_vp, _vp, _i, _f64],

@@ -1636,6 +1636,136 @@ struct b200_heat2d_plan_st
 namespace
 {
     // ---- the walker form of an S-level launch (heatWalkKernel), S = 4, 6, 8
+    // ---- host-side planning of a walker launch: windows, edge windows, front segments (slab strips / physical bands), interior
+    // segments. Pure arithmetic on the geometry already in A (loY, hiY, loX, hiX, ghost*, sendRows) -- no device needed, which is
+    // what b200_heat2d_walk_plan_query exposes to the CPU property tests. Fills the decomposition fields of A; `rowsInt`,
+    // `nInner` and `split` go back to the launcher. false: too many walkers.
+    struct WalkPlanExtra
+    {
+        int64_t rowsInt;
+        uint32_t nInner, nStrip;
+        bool split;
+    };
+
+    // Segments per window for `rowsInt` rows on `nslots` resident walkers: maximise (share of the slots used over all waves) x
+    // (share of a walker's rows that are not its 2S-row prologue) x waves / (waves + tail) -- the last factor models the tail a
+    // slower walker of the last wave leaves; it favours a few waves over exactly one.
+    int64_t pickWalkSegRows(int64_t rowsInt, int64_t windows, int64_t nslots, double tail, int S)
+    {
+        int64_t best = rowsInt;
+        double bestScore = -1.0;
+        int64_t const maxSeg = (rowsInt + 15) / 16;
+        for(int64_t k = 1; k <= maxSeg && k <= 8192; ++k)
+        {
+            int64_t const segRows = (rowsInt + k - 1) / k;
+            int64_t const segs = (rowsInt + segRows - 1) / segRows;
+            double const walkers = double(segs) * double(windows);
+            double const waves = double((int64_t(walkers) + nslots - 1) / nslots);
+            double const score = walkers / (waves * double(nslots)) * double(segRows) / double(segRows + 2 * S) * waves / (waves + tail);
+            if(score > bestScore + 1e-9)
+            {
+                bestScore = score;
+                best = segRows;
+            }
+        }
+        return best;
+    }
+
+    bool planWalk(HeatWArgs& A, int S, int64_t slots, bool splitOk, WalkPlanExtra& X)
+    {
+        int const LOST = (S + 3) / 4;
+        int const BOXX = 32 * kWalkCols;
+        int const WW = BOXX - 2 * kWalkCols * LOST;
+        // windows cover the columns 0 .. hiX + 1 (window w stores columns [w WW, (w+1) WW))
+        A.nWin = (uint32_t(A.hiX) + 2 + uint32_t(WW) - 1) / uint32_t(WW);
+        // bare windows (the kernel's colInterior): field data in all 128 columns, no ring column among them, core columns
+        // stored. The others -- window 0 and the last few -- are the edge windows, dispatched first.
+        auto const isBare = [&](uint32_t w)
+        {
+            int64_t const cx = int64_t(w) * WW - kWalkCols * LOST;
+            return cx >= A.loX - (A.ghostLeft ? A.loX : 0) && cx + BOXX - 1 <= A.hiX + (A.ghostRight ? A.loX : 0)
+                   && cx + kWalkCols * LOST >= A.loX && cx + BOXX - 1 - kWalkCols * LOST <= A.hiX;
+        };
+        A.nEdgeRight = 0;
+        while(A.nEdgeRight + 1 < A.nWin && !isBare(A.nWin - 1 - A.nEdgeRight))
+            ++A.nEdgeRight;
+        bool middleAllBare = true; // (window 0 is never bare: its first lanes lie left of column 0)
+        for(uint32_t w = 1; w + A.nEdgeRight < A.nWin; ++w)
+            middleAllBare = middleAllBare && isBare(w);
+        uint32_t const nEdge = 1u + A.nEdgeRight, nInner = A.nWin - nEdge;
+        // Split: the interior windows' interior rows go to the bare-only kernel (128 registers, 4 CTAs per SM), this kernel
+        // keeps the edge windows, the strips and the S-row bands next to a physical ring. Needs rows for both bands.
+        // Measured (profiles/r02/heat_walk_probe_split.log, 16384^2, 960 steps): 4 levels 215 us per step split (225 without the
+        // dependent-launch overlap) against 196 in one kernel, 6 levels 185 against 183 -- a fourth CTA per SM does not pay
+        // for the second launch and the shallower stage ring, so the split stays OFF by default.
+        bool const split = splitOk && nInner > 0 && middleAllBare && b200::tune("heat.walk_split", 0) != 0
+                           && int64_t(A.hiY) - A.loY + 1 >= int64_t(4 * S) + 2 * A.sendRows;
+        // output rows: the core rows, plus the ring row on a physical side
+        int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
+        A.nFront = 0;
+        A.frontIsStrip = 0;
+        uint32_t nStrip = 0;
+        if(A.ghostTop)
+        {
+            // strip: the rows sent to the upper neighbour
+            A.frontY0[A.nFront] = A.loY;
+            A.frontY1[A.nFront] = A.loY + A.sendRows;
+            A.frontIsStrip |= 1u << A.nFront;
+            outLo = A.loY + A.sendRows;
+            ++A.nFront;
+            ++nStrip;
+        }
+        else if(split)
+        {
+            // band: the ring row and the S - 1 core rows whose lower levels touch it
+            A.frontY0[A.nFront] = outLo;
+            A.frontY1[A.nFront] = A.loY + S - 1;
+            outLo = A.loY + S - 1;
+            ++A.nFront;
+        }
+        if(A.ghostBottom)
+        {
+            A.frontY0[A.nFront] = A.hiY + 1 - A.sendRows;
+            A.frontY1[A.nFront] = A.hiY + 1;
+            A.frontIsStrip |= 1u << A.nFront;
+            outHi = A.hiY - A.sendRows;
+            ++A.nFront;
+            ++nStrip;
+        }
+        else if(split)
+        {
+            A.frontY0[A.nFront] = A.hiY - S + 2;
+            A.frontY1[A.nFront] = outHi + 1;
+            outHi = A.hiY - S + 1;
+            ++A.nFront;
+        }
+        A.intY0 = outLo;
+        A.intY1 = outHi + 1;
+        int64_t const rowsInt = int64_t(A.intY1) - A.intY0;
+        int64_t const forced = b200::tune("heat.walk_seg_rows", 0);
+        uint32_t nSeg = 0;
+        A.segRows = 1;
+        if(rowsInt > 0)
+        {
+            // in split mode this kernel walks the interior rows with the edge windows only: short segments, so that it is over
+            // long before the bare-only kernel that runs next to it
+            A.segRows = int32_t(forced > 0 ? forced : (split ? std::min<int64_t>(rowsInt, 128) : pickWalkSegRows(rowsInt, A.nWin, slots, 0.3, S)));
+            nSeg = uint32_t((rowsInt + A.segRows - 1) / A.segRows);
+        }
+        A.nSegAll = A.nFront + nSeg;
+        uint64_t const walkers = split ? uint64_t(nEdge) * A.nSegAll + uint64_t(nInner) * A.nFront : uint64_t(A.nSegAll) * A.nWin;
+        if(walkers > 0x7fffffffull)
+            return false;
+        A.nWalkers = uint32_t(walkers);
+        A.stripTiles = nStrip * A.nWin; // strip WALKERS: each counts itself once
+        X.rowsInt = rowsInt;
+        X.nInner = nInner;
+        X.nStrip = nStrip;
+        X.split = split;
+        (void) walkers;
+        return true;
+    }
+
     // SPLIT_OK: this shape also exists as a bare-only kernel for the interior (instantiated for the default shapes only)
     template<int S, int R, int ST, int MINB, bool SWAP = false, bool SPLIT_OK = false>
     int launchWalkShape(b200_heat2d_plan_t plan, cudaStream_t s, int src_index, HeatWArgs& A, bool sq)
@@ -1690,110 +1820,15 @@ namespace
         }
         auto aligned32 = [](void const* p) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % 32 == 0; };
         A.align32 = plan->pitchBytes % 32 == 0 && aligned32(A.dst) && aligned32(A.peerDst[0]) && aligned32(A.peerDst[1]) ? 1 : 0;
-        // windows cover the columns 0 .. hiX + 1 (window w stores columns [w WW, (w+1) WW))
-        A.nWin = (uint32_t(A.hiX) + 2 + uint32_t(WW) - 1) / uint32_t(WW);
-        // bare windows (the kernel's colInterior): field data in all 128 columns, no ring column among them, core columns
-        // stored. The others -- window 0 and the last few -- are the edge windows, dispatched first.
-        auto const isBare = [&](uint32_t w)
-        {
-            int64_t const cx = int64_t(w) * WW - kWalkCols * WalkGeom<S>::LOST;
-            return cx >= A.loX - (A.ghostLeft ? A.loX : 0) && cx + BOXX - 1 <= A.hiX + (A.ghostRight ? A.loX : 0)
-                   && cx + kWalkCols * WalkGeom<S>::LOST >= A.loX && cx + BOXX - 1 - kWalkCols * WalkGeom<S>::LOST <= A.hiX;
-        };
-        A.nEdgeRight = 0;
-        while(A.nEdgeRight + 1 < A.nWin && !isBare(A.nWin - 1 - A.nEdgeRight))
-            ++A.nEdgeRight;
-        bool middleAllBare = true; // (window 0 is never bare: its first lanes lie left of column 0)
-        for(uint32_t w = 1; w + A.nEdgeRight < A.nWin; ++w)
-            middleAllBare = middleAllBare && isBare(w);
-        // Segments per window for `rowsInt` rows on `slots` resident walkers: maximise (share of the slots used over all
-        // waves) x (share of a walker's rows that are not its 2S-row prologue) x waves / (waves + tail) -- the last factor
-        // models the tail a slower walker of the last wave leaves; it favours a few waves over exactly one.
-        auto const pickSegRows = [&](int64_t rowsInt, int64_t windows, int64_t nslots, double tail) -> int64_t
-        {
-            int64_t best = rowsInt;
-            double bestScore = -1.0;
-            int64_t const maxSeg = (rowsInt + 15) / 16;
-            for(int64_t k = 1; k <= maxSeg && k <= 8192; ++k)
-            {
-                int64_t const segRows = (rowsInt + k - 1) / k;
-                int64_t const segs = (rowsInt + segRows - 1) / segRows;
-                double const walkers = double(segs) * double(windows);
-                double const waves = double((int64_t(walkers) + nslots - 1) / nslots);
-                double const score = walkers / (waves * double(nslots)) * double(segRows) / double(segRows + 2 * S) * waves / (waves + tail);
-                if(score > bestScore + 1e-9)
-                {
-                    bestScore = score;
-                    best = segRows;
-                }
-            }
-            return best;
-        };
-        uint32_t const nEdge = 1u + A.nEdgeRight, nInner = A.nWin - nEdge;
-        // Split: the interior windows' interior rows go to the bare-only kernel (128 registers, 4 CTAs per SM), this kernel
-        // keeps the edge windows, the strips and the S-row bands next to a physical ring. Needs rows for both bands.
-        // Measured (profiles/r02/heat_walk_probe_split.log, 16384^2, 960 steps): 4 levels 215 us per step split (225 without the
-        // dependent-launch overlap) against 196 in one kernel, 6 levels 185 against 183 -- a fourth CTA per SM does not pay
-        // for the second launch and the shallower stage ring, so the split stays OFF by default.
-        bool const split = SPLIT_OK && nInner > 0 && middleAllBare && b200::tune("heat.walk_split", 0) != 0
-                           && int64_t(A.hiY) - A.loY + 1 >= int64_t(4 * S) + 2 * A.sendRows;
-        // output rows: the core rows, plus the ring row on a physical side
-        int32_t outLo = A.loY - (A.ghostTop ? 0 : 1), outHi = A.hiY + (A.ghostBottom ? 0 : 1); // inclusive
-        A.nFront = 0;
-        A.frontIsStrip = 0;
-        uint32_t nStrip = 0;
-        if(A.ghostTop)
-        {
-            // strip: the rows sent to the upper neighbour
-            A.frontY0[A.nFront] = A.loY;
-            A.frontY1[A.nFront] = A.loY + A.sendRows;
-            A.frontIsStrip |= 1u << A.nFront;
-            outLo = A.loY + A.sendRows;
-            ++A.nFront;
-            ++nStrip;
-        }
-        else if(split)
-        {
-            // band: the ring row and the S - 1 core rows whose lower levels touch it
-            A.frontY0[A.nFront] = outLo;
-            A.frontY1[A.nFront] = A.loY + S - 1;
-            outLo = A.loY + S - 1;
-            ++A.nFront;
-        }
-        if(A.ghostBottom)
-        {
-            A.frontY0[A.nFront] = A.hiY + 1 - A.sendRows;
-            A.frontY1[A.nFront] = A.hiY + 1;
-            A.frontIsStrip |= 1u << A.nFront;
-            outHi = A.hiY - A.sendRows;
-            ++A.nFront;
-            ++nStrip;
-        }
-        else if(split)
-        {
-            A.frontY0[A.nFront] = A.hiY - S + 2;
-            A.frontY1[A.nFront] = outHi + 1;
-            outHi = A.hiY - S + 1;
-            ++A.nFront;
-        }
-        A.intY0 = outLo;
-        A.intY1 = outHi + 1;
-        int64_t const rowsInt = int64_t(A.intY1) - A.intY0;
+        WalkPlanExtra X{};
+        if(!planWalk(A, S, slots, SPLIT_OK, X))
+            return b200::fail(B200_ERANGE, "heat walker: too many walkers", __FILE__, __LINE__);
+        int64_t const rowsInt = X.rowsInt;
+        uint32_t const nInner = X.nInner;
+        bool const split = X.split;
+        uint64_t const walkers = A.nWalkers;
         int64_t const forced = b200::tune("heat.walk_seg_rows", 0);
-        uint32_t nSeg = 0;
-        A.segRows = 1;
-        if(rowsInt > 0)
-        {
-            // in split mode this kernel walks the interior rows with the edge windows only: short segments, so that it is over
-            // long before the bare-only kernel that runs next to it
-            A.segRows = int32_t(forced > 0 ? forced : (split ? std::min<int64_t>(rowsInt, 128) : pickSegRows(rowsInt, A.nWin, slots, 0.3)));
-            nSeg = uint32_t((rowsInt + A.segRows - 1) / A.segRows);
-        }
-        A.nSegAll = A.nFront + nSeg;
-        uint64_t const walkers = split ? uint64_t(nEdge) * A.nSegAll + uint64_t(nInner) * A.nFront : uint64_t(A.nSegAll) * A.nWin;
-        B200_REQUIRE(walkers <= 0x7fffffffull, B200_ERANGE);
-        A.nWalkers = uint32_t(walkers);
-        A.stripTiles = nStrip * A.nWin; // strip WALKERS: each counts itself once
+        auto const pickSegRows = [&](int64_t rows_, int64_t windows, int64_t nslots, double tail) { return pickWalkSegRows(rows_, windows, nslots, tail, S); };
         if(walkers > 0)
         {
             unsigned const grid = unsigned((walkers + kWalkWarps - 1) / kWalkWarps);
@@ -2554,6 +2589,54 @@ extern "C"
         unsigned const grid = unsigned(std::min<int64_t>(64, (cells + 255) / 256));
         haloColsKernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(H);
         B200_LAUNCH_CHECK();
+        return 0;
+    }
+
+    int b200_heat2d_walk_plan_query(
+        uint32_t ny,
+        uint32_t nx,
+        uint32_t pad_y,
+        uint32_t pad_x,
+        int edges,
+        int levels,
+        int resident_walkers,
+        b200_heat2d_walk_plan* out)
+    {
+        // the host-side decomposition of a walker launch, without a device (CPU property tests; tools)
+        B200_REQUIRE(out && ny >= 1 && nx >= 1 && pad_y >= 1 && pad_x >= 1 && resident_walkers >= 1, B200_EINVAL);
+        B200_REQUIRE((levels == 4 || levels == 6 || levels == 8) && (edges & ~B200_EDGE_ALL) == 0, B200_EINVAL);
+        HeatWArgs A{};
+        A.ny = ny;
+        A.nx = nx;
+        A.loY = int32_t(pad_y);
+        A.hiY = int32_t(ny + pad_y - 1);
+        A.loX = int32_t(pad_x);
+        A.hiX = int32_t(nx + pad_x - 1);
+        A.ghostTop = (edges & B200_EDGE_TOP) ? 0 : 1;
+        A.ghostBottom = (edges & B200_EDGE_BOTTOM) ? 0 : 1;
+        A.ghostLeft = (edges & B200_EDGE_LEFT) ? 0 : 1;
+        A.ghostRight = (edges & B200_EDGE_RIGHT) ? 0 : 1;
+        A.sendRows = int32_t(pad_y);
+        WalkPlanExtra X{};
+        if(!planWalk(A, levels, resident_walkers, levels != 8, X))
+            return b200::fail(B200_ERANGE, "heat walker: too many walkers", __FILE__, __LINE__);
+        int const lost = (levels + 3) / 4;
+        out->window_columns = uint32_t(32 * kWalkCols - 2 * kWalkCols * lost);
+        out->n_windows = A.nWin;
+        out->n_edge_right = A.nEdgeRight;
+        out->n_front = A.nFront;
+        out->front_is_strip = A.frontIsStrip;
+        for(int k = 0; k < 2; ++k)
+        {
+            out->front_y0[k] = A.frontY0[k];
+            out->front_y1[k] = A.frontY1[k];
+        }
+        out->interior_y0 = A.intY0;
+        out->interior_y1 = A.intY1;
+        out->segment_rows = A.segRows;
+        out->n_segments = A.nSegAll;
+        out->n_walkers = A.nWalkers;
+        out->split = X.split ? 1 : 0;
         return 0;
     }
 

@@ -61,6 +61,8 @@ namespace alpaka::b200
                 throw std::runtime_error("Heat2DStepper: the two fields must have identical extents (>= 3x3) and pitches");
             auto const ny = static_cast<std::uint32_t>(ext[0] - 2);
             auto const nx = static_cast<std::uint32_t>(ext[1] - 2);
+            // four levels per launch by default, eight on fields tall enough for long walks (as alpaka_b200.heat2d.Heat2D)
+            m_defaultDepth = ny >= 12288u && nx >= 4096u ? 8 : 4;
             constexpr double pi = math::constants::pi;
             // boundary factors on the HOST with the C library (the reference CPU back-end's values):
             // exactSolution(x, y, t) = exp(-pi*pi*t) * (sin(pi*x) + sin(pi*y)), analyticalSolution.hpp:17-21
@@ -130,11 +132,13 @@ namespace alpaka::b200
             queue.afterEnqueue();
         }
 
-        //! `n` steps with up to `depth` (1..8) time levels per launch; a remainder runs in shallower
+        //! `n` steps with up to `depth` (1..8; 0 = defaultDepth()) time levels per launch; a remainder runs in shallower
         //! launches (4 = 2 + 2 rather than 3 + 1)
         template<typename TQueue>
-        void steps(TQueue& queue, std::uint32_t n, int depth = 4)
+        void steps(TQueue& queue, std::uint32_t n, int depth = 0)
         {
+            if(depth == 0)
+                depth = m_defaultDepth;
             if(depth < 1 || depth > 8)
                 throw std::runtime_error("Heat2DStepper::steps: between 1 and 8 time levels per launch");
             while(n > 0)
@@ -159,10 +163,16 @@ namespace alpaka::b200
         {
             return m_step;
         }
+        //! time levels per launch that steps() aims for when it is not told
+        [[nodiscard]] auto defaultDepth() const -> int
+        {
+            return m_defaultDepth;
+        }
 
     private:
         b200_heat2d_plan_t m_plan = nullptr;
         double m_dt, m_rX, m_rY;
+        int m_defaultDepth = 4;
         int m_cur = 0;
         std::uint32_t m_step = 0;
     };

@@ -427,6 +427,23 @@ extern "C"
         uint32_t ghost, /* G */
         b200_heat2d_plan_t* out);
     int b200_heat2d_stepn_tile_f64(b200_heat2d_plan_t plan, b200_stream_t s, int src_index, double rx, double ry, int levels, double const* time_factors, uint32_t step);
+    /* The host-side decomposition of a walker launch (b200_heat2d_stepn_f64 / _halo_ / _tile_ at 4, 6, 8 levels) for a field of
+     * ny x nx core cells with ghost / ring depths pad_y, pad_x and `resident_walkers` walker slots on the device: column
+     * windows of `window_columns` stored columns (window w stores array columns [w * window_columns, ...)), of which window 0
+     * and the last n_edge_right are edge windows; per window n_front front segments (slab strips, bit k of front_is_strip;
+     * physical bands when the interior is split off) with output rows [front_y0[k], front_y1[k]) and the interior rows
+     * [interior_y0, interior_y1) cut into segments of segment_rows. No device needed: the CPU tests check that these segments
+     * cover every output row exactly once for any geometry. */
+    typedef struct b200_heat2d_walk_plan
+    {
+        uint32_t window_columns, n_windows, n_edge_right;
+        uint32_t n_front, front_is_strip;
+        int32_t front_y0[2], front_y1[2];
+        int32_t interior_y0, interior_y1, segment_rows;
+        uint32_t n_segments, n_walkers;
+        int32_t split;
+    } b200_heat2d_walk_plan;
+    int b200_heat2d_walk_plan_query(uint32_t ny, uint32_t nx, uint32_t pad_y, uint32_t pad_x, int edges, int levels, int resident_walkers, b200_heat2d_walk_plan* out);
     /* 0, or 1 + side of the first flag wait that timed out (a neighbour stopped making progress). Synchronous. */
     int b200_heat2d_halo_status(b200_heat2d_plan_t plan, uint32_t* status);
 
