@@ -1897,15 +1897,18 @@ namespace
             minb = levels == 4 ? 3 : 2;
         auto go = [&]<int S_, int R_, int ST_>() -> int
         {
-            // the default shape also exists with conflict-free loads (heat.walk_lds_swap)
-            bool const swap = R_ == 4 && ST_ == 4 && b200::tune("heat.walk_lds_swap", 0) != 0;
-            // (the default shape R4 x ST4 at the default register budget can split the interior off: SPLIT_OK, 4 and 6 levels)
+            // The default shape (R4 x ST4) exists at both register budgets, with conflict-free loads (heat.walk_lds_swap) and
+            // with the interior split off (SPLIT_OK; 4 and 6 levels); the three-stage shape at the default budget only.
+            // (Six-stage rings and two-row stages were measured slower and are no longer instantiated:
+            // profiles/r02/heat_walk_probe.log.)
+            constexpr bool kDefaultShape = R_ == 4 && ST_ == 4;
+            bool const swap = kDefaultShape && b200::tune("heat.walk_lds_swap", 0) != 0;
             if constexpr(S_ == 4)
             {
-                if(minb >= 4)
-                    return launchWalkShape<S_, R_, ST_, 4>(plan, s, src_index, A, sq);
-                if constexpr(R_ == 4 && ST_ == 4)
+                if constexpr(kDefaultShape)
                 {
+                    if(minb >= 4)
+                        return launchWalkShape<S_, R_, ST_, 4>(plan, s, src_index, A, sq);
                     if(swap)
                         return launchWalkShape<S_, R_, ST_, 3, true>(plan, s, src_index, A, sq);
                     return launchWalkShape<S_, R_, ST_, 3, false, true>(plan, s, src_index, A, sq);
@@ -1915,10 +1918,10 @@ namespace
             }
             else
             {
-                if(minb >= 3)
-                    return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
-                if constexpr(R_ == 4 && ST_ == 4)
+                if constexpr(kDefaultShape)
                 {
+                    if(minb >= 3)
+                        return launchWalkShape<S_, R_, ST_, 3>(plan, s, src_index, A, sq);
                     if(swap)
                         return launchWalkShape<S_, R_, ST_, 2, true>(plan, s, src_index, A, sq);
                     return launchWalkShape<S_, R_, ST_, 2, false, S_ == 6>(plan, s, src_index, A, sq);
@@ -1933,28 +1936,16 @@ namespace
             return go.template operator()<4, 4, 3>();
         case 444:
             return go.template operator()<4, 4, 4>();
-        case 426:
-            return go.template operator()<4, 2, 6>();
-        case 446:
-            return go.template operator()<4, 4, 6>();
         case 643:
             return go.template operator()<6, 4, 3>();
         case 644:
             return go.template operator()<6, 4, 4>();
-        case 626:
-            return go.template operator()<6, 2, 6>();
-        case 646:
-            return go.template operator()<6, 4, 6>();
         case 843:
             return go.template operator()<8, 4, 3>();
         case 844:
             return go.template operator()<8, 4, 4>();
-        case 826:
-            return go.template operator()<8, 2, 6>();
-        case 846:
-            return go.template operator()<8, 4, 6>();
         default:
-            return b200::fail(B200_EINVAL, "heat.walk_shape: supported 43, 44, 46, 26 (rows per stage x 10 + stages)", __FILE__, __LINE__);
+            return b200::fail(B200_EINVAL, "heat.walk_shape: supported 43, 44 (rows per stage x 10 + stages)", __FILE__, __LINE__);
         }
     }
 } // namespace

@@ -91,7 +91,7 @@ def test_heat2d_n_level_kernel_every_tile_shape(gpu, cfg):
 
 @pytest.mark.parametrize("split", [0, 1], ids=["one_kernel", "interior_in_bare_kernel"])
 @pytest.mark.parametrize("seg_rows", [0, 40, 7], ids=lambda r: f"seg{r}")
-@pytest.mark.parametrize("shape_key", [0, 43, 44, 46, 26], ids=lambda k: f"R{k // 10}_stages{k % 10}")
+@pytest.mark.parametrize("shape_key", [0, 43, 44], ids=lambda k: f"R{k // 10}_stages{k % 10}")
 @pytest.mark.parametrize("levels", [4, 6, 8])
 @pytest.mark.parametrize("square", [False, True], ids=["rx_ne_ry", "square_cells"])
 def test_heat2d_walker_kernel_every_shape(gpu, square, levels, shape_key, seg_rows, split):
