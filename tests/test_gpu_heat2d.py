@@ -261,3 +261,43 @@ def test_heat2d_argument_errors(gpu):
         ab.heat2d.Heat2D(queue, 0, 8, 0.1, 0.1, 1e-4)
     with pytest.raises(ab.B200Error):  # stability condition, heatEquation2D.cpp:67-73
         ab.heat2d.Heat2D(queue, 8, 8, 0.1, 0.1, 1.0)
+
+
+@pytest.mark.parametrize("levels", [4, 8])
+def test_heat2d_walker_rows_not_32_byte_aligned(gpu, levels):
+    """A row pitch that is a multiple of 16 but not of 32 bytes (the C ABI asks for 16): the walker's 256-bit stores are not
+    possible, every quad leaves as two 128-bit stores. Views over one raw allocation, the C ABI called directly."""
+    import ctypes as C
+
+    from alpaka_b200 import _lib
+    from alpaka_b200.runtime import Buf
+
+    ab, dev, queue = gpu
+    ny, nx = 90, 196  # (nx + 2) * 8 = 1584 = 99 * 16 bytes per row
+    pitch = (nx + 2) * 8
+    assert pitch % 16 == 0 and pitch % 32 != 0
+    dx, dy, dt = ol.heat_params(ny, nx)
+    u0 = ol.fill("uniform_f64", (ny + 2) * (nx + 2), seed=26).reshape(ny + 2, nx + 2)
+    steps = 2 * levels
+    want = ol.orc_heat_run(u0, 1, steps, dx, dy, dt)
+    raw = ab.alloc_buf(dev, np.float64, 2 * (ny + 2) * (nx + 2), queue)
+    views = [Buf(dev, np.float64, (ny + 2, nx + 2), native_ptr=raw.ptr + b * (ny + 2) * pitch, pitch_bytes=pitch) for b in range(2)]
+    for v in views:
+        ab.memcpy(queue, v, u0)
+    sx, sy = ab.heat2d.boundary_tables(ny, nx, dx, dy)
+    lib = _lib.load()
+    plan = C.c_void_p()
+    _lib.check(lib.b200_heat2d_plan_create(dev.idx, views[0].ptr, views[1].ptr, pitch, ny, nx, sx.ctypes.data, sy.ctypes.data, 15, C.byref(plan)))
+    try:
+        cur = 0
+        for launch in range(2):
+            tfs = (C.c_double * levels)(*[ab.heat2d.time_factor(launch * levels + 1 + l, dt) for l in range(levels)])
+            _lib.check(lib.b200_heat2d_stepn_f64(plan, queue.handle, cur, dt / (dx * dx), dt / (dy * dy), levels, tfs))
+            cur ^= 1
+        got = np.empty_like(u0)
+        ab.memcpy(queue, got, views[cur])
+        queue.wait()
+    finally:
+        lib.b200_heat2d_plan_destroy(plan)
+        raw.free()
+    assert got.tobytes() == want.tobytes()

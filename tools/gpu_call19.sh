@@ -1,4 +1,2 @@
 #!/bin/bash
-O=gpurun_out/r02; mkdir -p $O
-timeout 600 python -m pytest tests/test_gpu_heat2d.py tests/test_gpu_heat_halo.py tests/test_golden_multi.py -m gpu -x -q 2>&1 | tail -3
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python -m pytest tests/test_gpu_heat2d.py -m gpu -x -q -k "not_32_byte" 2>&1 | tail -12
