@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+namespace alpaka::b200
+{
     //! Time levels of the next launch when `n` steps are left and a launch may advance up to `depth`: the deepest depth
     //! the kernels support (1, 2, 3 tile kernels; 4, 6, 8 walker kernel) that does not leave a single step behind
     //! (4 = 2 + 2 rather than 3 + 1); `minDepth` = 2 for slabs. 0 if nothing fits.
@@ -33,8 +35,6 @@
         return 0;
     }
 
-namespace alpaka::b200
-{
     class Heat2DStepper
     {
     public:
