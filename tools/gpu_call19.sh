@@ -1,2 +1,2 @@
 #!/bin/bash
-timeout 300 python -m pytest tests/test_gpu_heat2d.py -m gpu -x -q -k "not_32_byte" 2>&1 | tail -12
+timeout 150 python -m pytest tests/test_gpu_cpp_layer.py -m gpu -x -q -k "heat2d" 2>&1 | tail -4
